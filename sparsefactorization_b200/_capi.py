@@ -1,0 +1,96 @@
+"""ctypes binding of libpsf_b200.so (include/psf_b200.h).  No CPU fallback: if the library is
+missing and cannot be built, importing the operators fails loudly."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+from . import build as _build
+
+PSF_OK = 0
+PSF_F32, PSF_F64 = 0, 1
+PATH_AUTO, PATH_GENERIC, PATH_FUSED = 0, 1, 2
+MAX_TAPS = 32
+
+
+class WStrides(C.Structure):
+    _fields_ = [("factor", C.c_int64), ("sample", C.c_int64), ("row", C.c_int64), ("tap", C.c_int64)]
+
+
+class ChainDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int64), ("n", C.c_int64), ("C", C.c_int64),
+        ("n_W", C.c_int), ("L", C.c_int), ("residual", C.c_int), ("dtype", C.c_int),
+        ("ws", WStrides),
+        ("offsets", C.POINTER(C.c_int64)),
+        ("path", C.c_int),
+    ]
+
+
+_lock = threading.Lock()
+_lib = None
+
+_SIGNATURES = {
+    "psf_version": (C.c_int, []),
+    "psf_error_string": (C.c_char_p, [C.c_int]),
+    "psf_chord_offsets": (C.c_int, [C.c_int64, C.c_int, C.POINTER(C.c_int64)]),
+    "psf_chord_indices_host": (C.c_int, [C.c_int64, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "psf_chord_indices_device": (C.c_int, [C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "psf_chord_mask_host": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "psf_factor_fwd": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int64,
+                                 C.c_int64, C.c_int, C.c_int64, C.c_void_p]),
+    "psf_factor_bwd": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.POINTER(C.c_int64), C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_void_p]),
+    "psf_chain_workspace_bytes": (C.c_size_t, [C.POINTER(ChainDesc), C.c_int]),
+    "psf_chain_fwd": (C.c_int, [C.POINTER(ChainDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                C.c_int, C.POINTER(C.c_int), C.c_void_p]),
+    "psf_chain_bwd": (C.c_int, [C.POINTER(ChainDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_size_t, C.POINTER(C.c_int), C.c_void_p]),
+    "psf_w_relayout": (C.c_int, [C.c_int, C.c_void_p, WStrides, C.c_void_p, WStrides, C.c_int, C.c_int64, C.c_int64,
+                                 C.c_int, C.c_void_p]),
+    "psf_chain_fused_plan": (C.c_int, [C.POINTER(ChainDesc), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                       C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load():
+    """Load (building first if the sources are newer) and type the library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB_PATH
+        if not os.path.exists(path):
+            try:
+                path = _build.build()
+            except Exception as exc:  # no nvcc on the box and no prebuilt library
+                raise ImportError(
+                    "libpsf_b200.so is missing and could not be built; run "
+                    "`python -m sparsefactorization_b200.build` where nvcc is available. "
+                    "There is no CPU fallback for the PSF chain.") from exc
+        lib = C.CDLL(path)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)   # AttributeError if the header and the library disagree
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+class PsfError(RuntimeError):
+    pass
+
+
+def check(status: int, what: str) -> None:
+    if status != PSF_OK:
+        msg = load().psf_error_string(status).decode()
+        raise PsfError(f"{what} failed with status {status}: {msg}")

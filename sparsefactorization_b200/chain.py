@@ -1,0 +1,179 @@
+"""The fused chord-factor chain as one autograd operator.
+
+Replaces the Python loop over ``torch_sparse.spmm`` in the reference's ``PSFNet.forward``
+(SyntheticExperiments/psf.py:167-188; LRA/psf.py:219-240): all ``n_W`` factors, forward and
+backward, are two calls into libpsf_b200.so.  CUDA only -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _capi
+
+_PATHS = {"auto": _capi.PATH_AUTO, "generic": _capi.PATH_GENERIC, "fused": _capi.PATH_FUSED}
+_PATH_NAMES = {v: k for k, v in _PATHS.items()}
+_DTYPES = {torch.float32: _capi.PSF_F32, torch.float64: _capi.PSF_F64}
+
+last_path_used: Optional[str] = None   # "fused" / "generic": which implementation the last forward took
+
+
+def _require_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError("sparsefactorization_b200: the PSF chain runs on CUDA only (no CPU fallback); "
+                               "got a tensor on %s" % t.device)
+
+
+def _offsets_array(offsets: Optional[Sequence[int]], L: int):
+    if offsets is None:
+        return None, None
+    if isinstance(offsets, torch.Tensor):
+        offsets = offsets.detach().cpu().tolist()
+    offsets = [int(o) for o in offsets]
+    if len(offsets) != L:
+        raise ValueError(f"need {L} offsets, got {len(offsets)}")
+    arr = (C.c_int64 * L)(*offsets)
+    return arr, offsets
+
+
+def _dense_nonoverlapping(t: torch.Tensor) -> bool:
+    # every stride order of a 4-d dense tensor is a permutation of a contiguous one
+    sizes_strides = sorted(((st, sz) for sz, st in zip(t.shape, t.stride()) if sz > 1))
+    expect = 1
+    for st, sz in sizes_strides:
+        if st != expect:
+            return False
+        expect *= sz
+    return True
+
+
+def _desc(W: torch.Tensor, V0: torch.Tensor, residual: bool, offs_arr, path: int) -> _capi.ChainDesc:
+    n_W, B, n, L = W.shape
+    d = _capi.ChainDesc()
+    d.B, d.n, d.C = B, n, V0.shape[2]
+    d.n_W, d.L = n_W, L
+    d.residual = 1 if residual else 0
+    d.dtype = _DTYPES[W.dtype]
+    sf, sb, sr, st = W.stride()
+    d.ws = _capi.WStrides(sf, sb, sr, st)
+    d.offsets = C.cast(offs_arr, C.POINTER(C.c_int64)) if offs_arr is not None else None
+    d.path = path
+    return d
+
+
+class _ChordChainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, W, V0, residual, offsets, path):
+        global last_path_used
+        lib = _capi.load()
+        _require_cuda(W, V0)
+        if W.dim() != 4 or V0.dim() != 3:
+            raise ValueError("W must be [n_W, B, n, L] and V0 [B, n, C]")
+        n_W, B, n, L = W.shape
+        if V0.shape[0] != B or V0.shape[1] != n:
+            raise ValueError(f"shape mismatch: W {tuple(W.shape)} vs V0 {tuple(V0.shape)}")
+        if W.dtype not in _DTYPES or V0.dtype != W.dtype:
+            raise TypeError("W and V0 must both be float32 or both float64")
+        if not _dense_nonoverlapping(W):
+            W = W.contiguous()
+        V0 = V0.contiguous()
+        offs_arr, offs_list = _offsets_array(offsets, L)
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        out = torch.empty_like(V0)
+        with torch.cuda.device(W.device):
+            d = _desc(W, V0, residual, offs_arr, _PATHS[path])
+            nbytes = lib.psf_chain_workspace_bytes(C.byref(d), 1 if need_grad else 0)
+            ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=W.device)
+            used = C.c_int(0)
+            stream = torch.cuda.current_stream().cuda_stream
+            rc = lib.psf_chain_fwd(C.byref(d), W.data_ptr(), V0.data_ptr(), out.data_ptr(), ws.data_ptr(),
+                                   ws.numel(), 1 if need_grad else 0, C.byref(used), stream)
+            _capi.check(rc, "psf_chain_fwd")
+        last_path_used = _PATH_NAMES.get(used.value, str(used.value))
+        if need_grad:
+            ctx.save_for_backward(W)
+            ctx.ws = ws
+            ctx.residual = residual
+            ctx.offs_list = offs_list
+            ctx.path_used = used.value
+            ctx.v_shape = V0.shape
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dOut):
+        lib = _capi.load()
+        (W,) = ctx.saved_tensors
+        dOut = dOut.contiguous()
+        L = W.shape[3]
+        offs_arr, _ = _offsets_array(ctx.offs_list, L)
+        dW = torch.empty_strided(W.shape, W.stride(), dtype=W.dtype, device=W.device)
+        dV0 = torch.empty(ctx.v_shape, dtype=W.dtype, device=W.device)
+        with torch.cuda.device(W.device):
+            V_like = dV0
+            d = _desc(W, V_like, ctx.residual, offs_arr, ctx.path_used)   # same path as the forward: state layout
+            used = C.c_int(0)
+            stream = torch.cuda.current_stream().cuda_stream
+            rc = lib.psf_chain_bwd(C.byref(d), W.data_ptr(), dOut.data_ptr(), dW.data_ptr(), dV0.data_ptr(),
+                                   ctx.ws.data_ptr(), ctx.ws.numel(), C.byref(used), stream)
+            _capi.check(rc, "psf_chain_bwd")
+        ctx.ws = None
+        return dW, dV0, None, None, None
+
+
+def chord_chain(W: torch.Tensor, V0: torch.Tensor, use_residuals: bool = False,
+                offsets: Optional[Sequence[int]] = None, path: str = "auto") -> torch.Tensor:
+    """Apply ``W[n_W-1] ... W[0]`` to ``V0``.
+
+    W  : logical shape ``[n_W, B, n, L]``, any dense stride order.  The streaming ("tap-major")
+         order -- physical ``[n_W, L, B, n]``, see :func:`empty_tap_major` -- is what the fused
+         kernel consumes directly; the reference order (physical ``[n_W, B, n, L]``) runs through
+         the per-factor path.
+    V0 : ``[B, n, C]``.   offsets: tap offsets (default chord: 0, 1, 2, 4, ... mod n).
+    Returns ``V_{n_W}`` with ``V_m = W_m V_{m-1} (+ V_0 if use_residuals)``.
+    """
+    return _ChordChainFn.apply(W, V0, bool(use_residuals), offsets, path)
+
+
+def empty_tap_major(n_W: int, B: int, n: int, L: int, dtype=torch.float32, device="cuda") -> torch.Tensor:
+    """Logical ``[n_W, B, n, L]`` view of a physical ``[n_W, L, B, n]`` buffer (row stride 1)."""
+    return torch.empty(n_W, L, B, n, dtype=dtype, device=device).permute(0, 2, 3, 1)
+
+
+def to_tap_major(W: torch.Tensor) -> torch.Tensor:
+    """Re-lay a logical ``[n_W, B, n, L]`` stack into the streaming order with the library's
+    tiled transpose (values unchanged).  Not differentiable; for benches and tests."""
+    lib = _capi.load()
+    _require_cuda(W)
+    n_W, B, n, L = W.shape
+    dst = empty_tap_major(n_W, B, n, L, W.dtype, W.device)
+    with torch.cuda.device(W.device):
+        rc = lib.psf_w_relayout(_DTYPES[W.dtype], W.data_ptr(), _capi.WStrides(*W.stride()), dst.data_ptr(),
+                                _capi.WStrides(*dst.stride()), n_W, B, n, L, torch.cuda.current_stream().cuda_stream)
+        _capi.check(rc, "psf_w_relayout")
+    return dst
+
+
+def chord_chain_list(Ws: Sequence[torch.Tensor], V0: torch.Tensor, use_residuals: bool = False,
+                     offsets: Optional[Sequence[int]] = None, path: str = "auto") -> torch.Tensor:
+    """Convenience for reference-shaped inputs: ``Ws[m]`` is ``[B, n, L]`` as ``fs[m](data)`` returns."""
+    return chord_chain(torch.stack(list(Ws), 0), V0, use_residuals, offsets, path)
+
+
+def fused_plan(n_W: int, B: int, n: int, L: int, C_: int = 8, residual: bool = True):
+    """Launch geometry of the fused path for a tap-major problem, or None if unsupported."""
+    lib = _capi.load()
+    d = _capi.ChainDesc()
+    d.B, d.n, d.C, d.n_W, d.L, d.residual, d.dtype = B, n, C_, n_W, L, int(residual), _capi.PSF_F32
+    d.ws = _capi.WStrides(L * B * n, n, 1, B * n)
+    d.offsets = None
+    d.path = _capi.PATH_AUTO
+    vals = [C.c_int(0) for _ in range(5)]
+    rc = lib.psf_chain_fused_plan(C.byref(d), *[C.byref(v) for v in vals])
+    if rc != 0:
+        return None
+    keys = ("cluster", "rows_per_cta", "threads", "smem_bytes", "resident_clusters")
+    return dict(zip(keys, (v.value for v in vals)))

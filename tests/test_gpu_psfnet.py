@@ -1,0 +1,103 @@
+"""Module-level parity on the GPU: the drop-in PSFNet variants against the golden vectors the
+reference's own modules produced (logits, loss, every parameter gradient)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(case):
+    from sparsefactorization_b200.psf import PSFNet as SynPSFNet
+    from sparsefactorization_b200.lra.psf import PSFNet as LraPSFNet
+    if case == "adding_n128":      # synthetic_training_config.py:4-18 at n=128 (BASELINE cfg1)
+        return SynPSFNet(vocab_size=1, add_init_linear_layer=True, embedding_size=32, n_vec=128, n_W=7,
+                         Ws=[32, "GELU"], V=[32, "GELU"], n_channels_V=8, n_class=1, pooling_type="FLATTEN",
+                         head=["linear"], use_cuda=True, use_residuals=True, use_pos_embedding=False,
+                         problem="adding"), torch.nn.MSELoss(), True, "fused"
+    if case == "order_n64":
+        return SynPSFNet(vocab_size=6, add_init_linear_layer=False, embedding_size=32, n_vec=64, n_W=6,
+                         Ws=[32, "GELU"], V=[32, "GELU"], n_channels_V=8, n_class=4, pooling_type="FLATTEN",
+                         head=["linear"], use_cuda=True, use_residuals=True, use_pos_embedding=True,
+                         problem="order"), torch.nn.CrossEntropyLoss(), True, "fused"
+    if case == "listops_n100":
+        return LraPSFNet(vocab_size=17, embedding_size=24, n_vec=100, n_W=7, Ws=[16, "GELU"], V=[16, "GELU"],
+                         n_channels_V=16, n_class=10, pooling_type="CLS", head=["linear"], use_cuda=True,
+                         use_residuals=False, dropout1_p=0, dropout2_p=0, dropout3_p=0,
+                         init_embedding_weights=False, use_pos_embedding=True,
+                         problem="listops"), torch.nn.CrossEntropyLoss(), False, "generic"
+    if case == "pathfinder_n64_duptap":
+        return LraPSFNet(vocab_size=225, embedding_size=16, n_vec=64, n_W=7, Ws=[16, "GELU"], V=[16, "GELU"],
+                         n_channels_V=8, n_class=2, pooling_type="FLATTEN", head=["non-linear", 12], use_cuda=True,
+                         use_residuals=False, dropout1_p=0, dropout2_p=0, dropout3_p=0,
+                         init_embedding_weights=True, use_pos_embedding=True,
+                         problem="pathfinder"), torch.nn.CrossEntropyLoss(), False, "fused"
+    raise KeyError(case)
+
+
+@pytest.mark.parametrize("case", ["adding_n128", "order_n64", "listops_n100", "pathfinder_n64_duptap"])
+def test_psfnet_matches_reference_golden(case):
+    from sparsefactorization_b200 import chain
+    z = load_golden(f"psfnet_{case}.npz")
+    net, loss_fn, squeeze, want_path = _build(case)
+    sd = {k[len("param/"):]: torch.from_numpy(v) for k, v in z.items() if k.startswith("param/")}
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda()
+    assert net.chord_indicies.is_cuda and net.chord_indicies.dtype == torch.int64
+    X, Y = torch.from_numpy(z["X"]).cuda(), torch.from_numpy(z["Y"]).cuda()
+    pred = net(X)
+    assert chain.last_path_used == want_path
+    loss = loss_fn(pred.squeeze() if squeeze else pred, Y)
+    loss.backward()
+    np.testing.assert_allclose(pred.detach().cpu().numpy(), z["pred"], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(loss.detach().cpu().numpy(), z["loss"], rtol=1e-5, atol=1e-6)
+    grads = {k[len("grad/"):]: v for k, v in z.items() if k.startswith("grad/")}
+    for k, p in net.named_parameters():
+        if k in grads:
+            scale = max(1e-6, 1e-5 * float(np.abs(grads[k]).max()))
+            np.testing.assert_allclose(p.grad.cpu().numpy(), grads[k], rtol=1e-4, atol=scale, err_msg=k)
+        else:
+            assert p.grad is None or float(p.grad.abs().sum()) == 0.0, k
+
+
+def test_generate_factors_matches_per_module_call():
+    from sparsefactorization_b200._psfnet import MLPBlock, generate_factors
+    torch.manual_seed(0)
+    fs = torch.nn.ModuleList([MLPBlock([32, "GELU"], 32, 15) for _ in range(5)]).cuda()
+    data = torch.randn(3, 256, 32, device="cuda")
+    W = generate_factors(fs, data)
+    assert W.shape == (5, 3, 256, 15) and W.stride(2) == 1          # tap-major: row index innermost
+    for m, f in enumerate(fs):
+        torch.testing.assert_close(W[m], f(data), rtol=1e-5, atol=1e-6)
+    # deeper / GELU-free generator configs still batch
+    fs2 = torch.nn.ModuleList([MLPBlock([16, "GELU", 24, "GELU"], 32, 9) for _ in range(3)]).cuda()
+    W2 = generate_factors(fs2, data)
+    for m, f in enumerate(fs2):
+        torch.testing.assert_close(W2[m], f(data), rtol=1e-5, atol=1e-6)
+    fs3 = torch.nn.ModuleList([MLPBlock([], 32, 9) for _ in range(2)]).cuda()
+    W3 = generate_factors(fs3, data)
+    for m, f in enumerate(fs3):
+        torch.testing.assert_close(W3[m], f(data), rtol=1e-5, atol=1e-6)
+
+
+def test_train_model_loop_learns_adding_small():
+    """TrainModel end to end on a tiny Adding problem: loss must drop (smoke-level learning check)."""
+    from torch.utils.data import DataLoader
+    from sparsefactorization_b200 import data as D
+    from sparsefactorization_b200.psf import PSFNet
+    from sparsefactorization_b200.psf_utils import DatasetCreator, TrainModel, count_params, seed_everything
+    seed_everything(42)
+    n = 128
+    net = PSFNet(1, True, 32, n, 7, [32, "GELU"], [32, "GELU"], 8, 1, "FLATTEN", ["linear"], True, True, False,
+                 "adding").cuda()
+    assert count_params(net) == 15809
+    X, Y = D.adding(640, n, seed=1)
+    Xv, Yv = D.adding(80, n, seed=2)
+    mk = lambda a, b, sh: DataLoader(DatasetCreator(a, b), batch_size=40, shuffle=sh, drop_last=True)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    hist = TrainModel(net, mk(X, Y, True), mk(Xv, Yv, False), mk(Xv, Yv, False), 3, 1, opt, torch.nn.MSELoss(),
+                      "adding", saving_criteria=1000.0)
+    assert len(hist) == 3 and hist[-1]["train_loss"] < hist[0]["train_loss"]
+    assert np.isfinite(hist[-1]["test_loss"])
