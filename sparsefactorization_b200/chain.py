@@ -120,7 +120,6 @@ class _ChordChainFn(torch.autograd.Function):
             rc = lib.psf_chain_bwd(C.byref(d), W.data_ptr(), dOut.data_ptr(), dW.data_ptr(), dV0.data_ptr(),
                                    ctx.ws.data_ptr(), ctx.ws.numel(), C.byref(used), stream)
             _capi.check(rc, "psf_chain_bwd")
-        ctx.ws = None
         return dW, dV0, None, None, None
 
 

@@ -176,8 +176,8 @@ int psf_chain_fwd(const psf_chain_desc* d, const void* W, const void* V0, void* 
   PsfChainArgs a;
   int rc = make_args(d, &a);
   if (rc) return rc;
-  if (V0 == nullptr || out == nullptr || (W == nullptr && a.n_W > 0)) return PSF_ERR_ARG;
   if (a.B == 0) return PSF_OK;
+  if (V0 == nullptr || out == nullptr || (W == nullptr && a.n_W > 0)) return PSF_ERR_ARG;
   if (workspace == nullptr || workspace_bytes < psf_chain_workspace_bytes(d, save_states)) return PSF_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   int status;
@@ -199,8 +199,8 @@ int psf_chain_bwd(const psf_chain_desc* d, const void* W, const void* dOut, void
   PsfChainArgs a;
   int rc = make_args(d, &a);
   if (rc) return rc;
-  if (dOut == nullptr || dV0 == nullptr || ((W == nullptr || dW == nullptr) && a.n_W > 0)) return PSF_ERR_ARG;
   if (a.B == 0) return PSF_OK;
+  if (dOut == nullptr || dV0 == nullptr || ((W == nullptr || dW == nullptr) && a.n_W > 0)) return PSF_ERR_ARG;
   if (workspace == nullptr || workspace_bytes < psf_chain_workspace_bytes(d, 1)) return PSF_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   int status;
