@@ -2,11 +2,13 @@
 //
 // One thread-block CLUSTER owns one sample.  CTA q of a P-CTA cluster owns the contiguous row
 // block [q*RB, (q+1)*RB) for ALL channels and keeps it in shared memory, channel-major
-// ([C][RB] fp32, <= 128 KB), across all n_W factors.  Facts the layout is built on:
+// ([C][RB] fp32), across all n_W factors.  Facts the design is built on:
 //   * chord links only point forward (row i reads rows i+o_k, o_k >= 0), so a block can be
 //     updated IN PLACE by an ascending sweep over 128-row warp tiles (descending for the
 //     backward pass, whose links point backward): once a tile has been read by itself and by
-//     every lower tile, nobody inside the CTA needs its old value again.
+//     every lower tile, nobody inside the CTA needs its old value again.  No ping-pong buffer,
+//     so a 2048-row block costs 64 KB and two CTAs (of different samples) share an SM: while one
+//     waits at a barrier the other computes.
 //   * operands that fall outside the CTA's block (big taps, the halo of small taps, the cyclic
 //     wrap) are read from the previous state in global memory.  That state was written by the
 //     sibling CTAs a few microseconds earlier and is L2 resident; a hardware cluster barrier
@@ -17,25 +19,34 @@
 //     own runs with cp.async.bulk (TMA, 1-D) into a private 3-stage ring guarded by mbarriers;
 //     no producer warp, no cross-warp coupling, chord offsets are arithmetic (no COO gathers).
 //   * every thread owns 4 consecutive rows x 8 channels: all shared/global operand accesses
-//     are 128-bit and conflict free (consecutive lanes -> consecutive 16 B), taps whose offset
-//     is not a multiple of 4 (1 and 2) fall back to 32-bit accesses at the same byte cost.
+//     are 128-bit and bank-conflict free (consecutive lanes -> consecutive 16 B).  Taps whose
+//     offset is not a multiple of 4 read the two aligned quads that cover them and select in
+//     registers; in the forward pass taps {0,1,2,4} share the same two quads (13 instead of 15
+//     operand loads per row group and channel).
+//   * global (remote / residual) operand loads are issued one tap group ahead and consumed after
+//     the following local taps ("pending" slot); taps are visited big-offset-first, interleaved
+//     with small ones, so that every remote tap has local work to hide behind.
 //   * backward (output-stationary at row j):  one shifted read of G_m[j-o_k,:] feeds both
 //     dV_{m-1}[j,:] += W_m[j-o_k,k] * G_m[j-o_k,:]  and  dW_m[j-o_k,k] = <G_m[j-o_k,:], V_{m-1}[j,:]>,
 //     all C channels live in one thread so dW needs no cross-CTA reduction and is written once.
 //
 // Reference semantics: SyntheticExperiments/psf.py:167-188 (loop + residual), spmul_cuda.cu:24,
 // :79-80, :105-108 (per-factor formulas).
+#include <cstdlib>
+
 #include "psf_internal.cuh"
 
 namespace {
 
-constexpr int CT = 8;            // channels held per thread == C of the fast path
-constexpr int kTile = 128;       // rows per warp tile (32 lanes x 4 rows)
-constexpr int kStages = 3;       // W ring depth per warp
-constexpr int kTps = 3;          // taps per ring stage
-constexpr int kSlot = kTile + 8; // floats per tap slot (8 spare: shifted, 16 B aligned copies in bwd)
+constexpr int CT = 8;        // channels held per thread == C of the fast path
+constexpr int kTile = 128;   // rows per warp tile (32 lanes x 4 rows)
+constexpr int kMaxStages = 8; // W ring depth per warp is a launch parameter (<= 8)
 constexpr int kMaxThreads = 512;
-constexpr int kMaxBlockRows = 4096;  // 8 ch * 4096 rows * 4 B = 128 KB
+
+// ring geometry: forward stages 4 taps (the {0,1,2,4} head group is one stage) of exactly one tile;
+// backward stages 3 taps with 8 spare floats (shifted, 16 B aligned source windows).
+constexpr int kTpsF = 4, kSlotF = kTile;
+constexpr int kTpsB = 3, kSlotB = kTile + 8;
 
 struct FusedParams {
   const float* W;
@@ -48,7 +59,12 @@ struct FusedParams {
   int64_t sWf, sWb, sWt;
   int B, n, n_W, L, residual, save_states;
   int P, RB;
-  PsfOffsets offs;
+  int head;           // fwd: order[0..3] are the taps with offsets 0,1,2,4
+  int stages;         // W ring depth per warp
+  PsfOffsets offs;    // offset of tap k (mod n)
+  PsfOffsets order;   // order[i] = tap visited i-th
+  PsfOffsets ooffs;   // ooffs[i] = offs[order[i]]
+  long long tapoff[PSF_MAX_TAPS];  // order[i] * sWt (elements)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -93,17 +109,39 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 
 __device__ __forceinline__ float4 ld_cg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ float ld_cg1(const float* p) { return __ldcg(p); }
 __device__ __forceinline__ void st_cg4(float* p, float4 v) { __stcg(reinterpret_cast<float4*>(p), v); }
 __device__ __forceinline__ void st_cs4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
+__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
+// acc += a * b on 4 lanes as two packed fma.rn.f32x2 (FFMA2 on sm_100): half the FMA issue slots
 __device__ __forceinline__ void fma4(float4& acc, const float4& a, const float4& b) {
-  acc.x = fmaf(a.x, b.x, acc.x);
-  acc.y = fmaf(a.y, b.y, acc.y);
-  acc.z = fmaf(a.z, b.z, acc.z);
-  acc.w = fmaf(a.w, b.w, acc.w);
+  unsigned long long* pc = reinterpret_cast<unsigned long long*>(&acc);
+  const unsigned long long* pa = reinterpret_cast<const unsigned long long*>(&a);
+  const unsigned long long* pb = reinterpret_cast<const unsigned long long*>(&b);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(pc[0]) : "l"(pa[0]), "l"(pb[0]));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(pc[1]) : "l"(pa[1]), "l"(pb[1]));
 }
-__device__ __forceinline__ float& f4at(float4& v, int r) { return reinterpret_cast<float*>(&v)[r]; }
+__device__ __forceinline__ void fma2(float& c0, float& c1, float a0, float a1, float b0, float b1) {
+  float2 c = make_float2(c0, c1), a = make_float2(a0, a1), b = make_float2(b0, b1);
+  unsigned long long* pc = reinterpret_cast<unsigned long long*>(&c);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;"
+      : "+l"(*pc)
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  c0 = c.x;
+  c1 = c.y;
+}
+__device__ __forceinline__ void add4(float4& acc, const float4& a) {
+  acc.x += a.x;
+  acc.y += a.y;
+  acc.z += a.z;
+  acc.w += a.w;
+}
+// rows [s, s+4) out of the two aligned quads X = rows [0,4), Y = rows [4,8); s in 1..3 (warp-uniform)
+__device__ __forceinline__ float4 select_quad(const float4& X, const float4& Y, int s) {
+  if (s == 1) return make_float4(X.y, X.z, X.w, Y.x);
+  if (s == 2) return make_float4(X.z, X.w, Y.x, Y.y);
+  return make_float4(X.w, Y.x, Y.y, Y.z);
+}
 
 // Natural [row][8] <-> per-thread channel planes (4 rows x 8 channels), pure register shuffling.
 __device__ __forceinline__ void load_rows_natural(const float* __restrict__ base, float4 (&pl)[CT]) {
@@ -138,10 +176,11 @@ __device__ __forceinline__ void store_rows_natural(float* __restrict__ base, con
 //   for sample b (this cluster's samples) / factor m / chunk c (tiles of this warp) / tap group tg.
 // kBackward: m and c run downwards, and the staged rows are shifted by -o_k.
 // ---------------------------------------------------------------------------------------------
-template <bool kBackward>
 struct WCursor {
   int b, m, c, tg;
   bool valid;
+  int row0, rw;        // first row / rows of the tile being staged
+  const float* wptr;   // W + (m-1)*sWf + b*sWb (+ row0 in the forward pass)
 };
 
 struct WarpGeom {
@@ -149,92 +188,11 @@ struct WarpGeom {
   int blk_start, blk_end;  // rows of this CTA
   int ntiles;              // 128-row tiles in the block
   int nchunks;             // ceil(ntiles / nwarps)
-  int ngroups;             // ceil(L / kTps)
+  int ngroups;             // ceil(L / taps per stage)
   int cid, ncl;            // cluster id, number of clusters
 };
 
-template <bool kBackward>
-__device__ __forceinline__ int last_chunk_of_warp(const WarpGeom& g) {
-  // largest c with c*nwarps + warp < ntiles (>= 0 because the warp has work)
-  return (g.ntiles - 1 - g.warp) / g.nwarps;
-}
-
-template <bool kBackward>
-__device__ __forceinline__ void cursor_init(WCursor<kBackward>& cur, const FusedParams& p, const WarpGeom& g) {
-  cur.b = g.cid;
-  cur.tg = 0;
-  cur.valid = (g.warp < g.ntiles) && (cur.b < p.B) && (p.n_W > 0);
-  if (kBackward) {
-    cur.m = p.n_W;
-    cur.c = cur.valid ? last_chunk_of_warp<kBackward>(g) : 0;
-  } else {
-    cur.m = 1;
-    cur.c = 0;
-  }
-}
-
-template <bool kBackward>
-__device__ __forceinline__ void cursor_next(WCursor<kBackward>& cur, const FusedParams& p, const WarpGeom& g) {
-  if (++cur.tg < g.ngroups) return;
-  cur.tg = 0;
-  if (kBackward) {
-    if (--cur.c >= 0) return;
-    cur.c = last_chunk_of_warp<kBackward>(g);
-    if (--cur.m >= 1) return;
-    cur.m = p.n_W;
-  } else {
-    ++cur.c;
-    if (cur.c * g.nwarps + g.warp < g.ntiles) return;
-    cur.c = 0;
-    if (++cur.m <= p.n_W) return;
-    cur.m = 1;
-  }
-  cur.b += g.ncl;
-  cur.valid = cur.b < p.B;
-}
-
-// Lane 0: arm the stage barrier and launch the bulk copies of one stage (<= kTps taps).
-template <bool kBackward>
-__device__ __forceinline__ void issue_stage(const WCursor<kBackward>& cur, const FusedParams& p, const WarpGeom& g,
-                                            float* slot_base, uint32_t bar) {
-  const int tile = cur.c * g.nwarps + g.warp;
-  const int row0 = g.blk_start + tile * kTile;
-  const int rw = min(kTile, g.blk_end - row0);
-  const int k0 = cur.tg * kTps;
-  const int kn = min(kTps, p.L - k0);
-  const float* wbase = p.W + (int64_t)(cur.m - 1) * p.sWf + (int64_t)cur.b * p.sWb;
-  // bytes first (expect_tx must precede the copies)
-  uint32_t total = 0;
-  for (int t = 0; t < kn; ++t) {
-    const int o = p.offs.o[k0 + t];
-    total += (uint32_t)((kBackward && (o & 3)) ? rw + 4 : rw) * 4u;
-  }
-  mbar_expect_tx(bar, total);
-  for (int t = 0; t < kn; ++t) {
-    const int k = k0 + t;
-    const float* wk = wbase + (int64_t)k * p.sWt;
-    const uint32_t dst = smem_u32(slot_base + t * kSlot);
-    if (!kBackward) {
-      tma_load_1d(dst, wk + row0, (uint32_t)rw * 4u, bar);
-    } else {
-      const int o = p.offs.o[k];
-      int s0 = row0 - o;
-      if (s0 < 0) s0 += p.n;
-      const int a0 = s0 & ~3;                      // 16 B aligned start
-      const int len = (o & 3) ? rw + 4 : rw;       // floats
-      const int first = min(len, p.n - a0);        // before the cyclic wrap
-      tma_load_1d(dst, wk + a0, (uint32_t)first * 4u, bar);
-      if (first < len) tma_load_1d(dst + (uint32_t)first * 4u, wk, (uint32_t)(len - first) * 4u, bar);
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Forward
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kMaxThreads, 1) psf_chain_fwd_kernel(const FusedParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  WarpGeom g;
+__device__ __forceinline__ void make_geom(WarpGeom& g, const FusedParams& p, int tps) {
   g.warp = threadIdx.x >> 5;
   g.lane = threadIdx.x & 31;
   g.nwarps = blockDim.x >> 5;
@@ -245,31 +203,133 @@ __global__ void __launch_bounds__(kMaxThreads, 1) psf_chain_fwd_kernel(const Fus
   g.blk_end = min(p.n, g.blk_start + p.RB);
   g.ntiles = (g.blk_end - g.blk_start + kTile - 1) / kTile;
   g.nchunks = (g.ntiles + g.nwarps - 1) / g.nwarps;
-  g.ngroups = (p.L + kTps - 1) / kTps;
+  g.ngroups = (p.L + tps - 1) / tps;
+}
 
-  float* Vs = reinterpret_cast<float*>(smem_raw);  // [CT][RB]
-  const int RB = p.RB;
-  float* ring = Vs + CT * RB + (size_t)g.warp * kStages * kTps * kSlot;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Vs + CT * RB + (size_t)g.nwarps * kStages * kTps * kSlot) + g.warp * kStages;
+__device__ __forceinline__ int last_chunk_of_warp(const WarpGeom& g) {
+  return (g.ntiles - 1 - g.warp) / g.nwarps;  // largest c with c*nwarps + warp < ntiles
+}
 
+template <bool kBackward>
+__device__ __forceinline__ void cursor_tile(WCursor& cur, const FusedParams& p, const WarpGeom& g) {
+  const int tile = cur.c * g.nwarps + g.warp;
+  cur.row0 = g.blk_start + tile * kTile;
+  cur.rw = min(kTile, g.blk_end - cur.row0);
+  cur.wptr = p.W + (long long)(cur.m - 1) * p.sWf + (long long)cur.b * p.sWb + (kBackward ? 0 : cur.row0);
+}
+
+template <bool kBackward>
+__device__ __forceinline__ void cursor_init(WCursor& cur, const FusedParams& p, const WarpGeom& g) {
+  cur.b = g.cid;
+  cur.tg = 0;
+  cur.valid = (g.warp < g.ntiles) && (cur.b < p.B) && (p.n_W > 0);
+  if (kBackward) {
+    cur.m = p.n_W;
+    cur.c = cur.valid ? last_chunk_of_warp(g) : 0;
+  } else {
+    cur.m = 1;
+    cur.c = 0;
+  }
+  if (cur.valid) cursor_tile<kBackward>(cur, p, g);
+}
+
+template <bool kBackward>
+__device__ __forceinline__ void cursor_next(WCursor& cur, const FusedParams& p, const WarpGeom& g) {
+  if (++cur.tg < g.ngroups) return;
+  cur.tg = 0;
+  bool wrapped = false;
+  if (kBackward) {
+    if (--cur.c < 0) {
+      cur.c = last_chunk_of_warp(g);
+      if (--cur.m < 1) {
+        cur.m = p.n_W;
+        wrapped = true;
+      }
+    }
+  } else {
+    ++cur.c;
+    if (cur.c * g.nwarps + g.warp >= g.ntiles) {
+      cur.c = 0;
+      if (++cur.m > p.n_W) {
+        cur.m = 1;
+        wrapped = true;
+      }
+    }
+  }
+  if (wrapped) {
+    cur.b += g.ncl;
+    cur.valid = cur.b < p.B;
+  }
+  if (cur.valid) cursor_tile<kBackward>(cur, p, g);
+}
+
+// Lane 0: arm the stage barrier and launch the bulk copies of one stage (<= kTps taps).
+template <bool kBackward, int kTps, int kSlot>
+__device__ __forceinline__ void issue_stage(const WCursor& cur, const FusedParams& p, uint32_t dst, uint32_t bar) {
+  const int i0 = cur.tg * kTps;
+  if (!kBackward) {
+    const uint32_t bytes = (uint32_t)cur.rw * 4u;
+    const int kn = min(kTps, p.L - i0);
+    mbar_expect_tx(bar, bytes * (uint32_t)kn);
+#pragma unroll
+    for (int t = 0; t < kTps; ++t)
+      if (t < kn) tma_load_1d(dst + t * kSlot * 4, cur.wptr + p.tapoff[i0 + t], bytes, bar);
+  } else {
+    uint32_t total = 0;
+#pragma unroll
+    for (int t = 0; t < kTps; ++t)
+      if (i0 + t < p.L) total += (uint32_t)(cur.rw + ((p.ooffs.o[i0 + t] & 3) ? 4 : 0)) * 4u;
+    mbar_expect_tx(bar, total);
+#pragma unroll
+    for (int t = 0; t < kTps; ++t) {
+      if (i0 + t < p.L) {
+        const int o = p.ooffs.o[i0 + t];
+        int s0 = cur.row0 - o;
+        if (s0 < 0) s0 += p.n;
+        const int a0 = s0 & ~3;                      // 16 B aligned start of the source window
+        const int len = cur.rw + ((o & 3) ? 4 : 0);  // floats
+        const int first = min(len, p.n - a0);        // part before the cyclic wrap
+        const float* wk = cur.wptr + p.tapoff[i0 + t];
+        tma_load_1d(dst + t * kSlot * 4, wk + a0, (uint32_t)first * 4u, bar);
+        if (first < len) tma_load_1d(dst + (t * kSlot + first) * 4, wk, (uint32_t)(len - first) * 4u, bar);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward
+// ---------------------------------------------------------------------------------------------
+template <int kPlane>
+__global__ void __launch_bounds__(kMaxThreads, 1) psf_chain_fwd_kernel(const FusedParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int kTps = kTpsF, kSlot = kSlotF;
+  WarpGeom g;
+  make_geom(g, p, kTps);
+
+  float* Vs = reinterpret_cast<float*>(smem_raw);  // [CT][kPlane], rows [0, p.RB) of every plane in use
+  constexpr int RB = kPlane;                       // compile-time plane stride -> immediate LDS offsets
+  const int S = p.stages;
+  float* ring = Vs + CT * RB + (size_t)g.warp * S * kTps * kSlot;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Vs + CT * RB + (size_t)g.nwarps * S * kTps * kSlot) + g.warp * S;
+
+  const uint32_t ring_u32 = smem_u32(ring), bars_u32 = smem_u32(bars);
   if (g.lane == 0) {
-    for (int s = 0; s < kStages; ++s) mbar_init(smem_u32(&bars[s]), 1);
+    for (int s = 0; s < S; ++s) mbar_init(bars_u32 + s * 8, 1);
     fence_barrier_init();
   }
   __syncwarp();
 
-  // prime the ring
-  WCursor<false> cur;
-  cursor_init(cur, p, g);
-  int issued = 0;
-  for (int s = 0; s < kStages; ++s) {
+  WCursor cur;
+  cursor_init<false>(cur, p, g);
+  for (int s = 0; s < S; ++s) {  // prime the ring
     if (cur.valid) {
-      if (g.lane == 0) issue_stage(cur, p, g, ring + s * kTps * kSlot, smem_u32(&bars[s]));
-      cursor_next(cur, p, g);
-      ++issued;
+      if (g.lane == 0) issue_stage<false, kTps, kSlot>(cur, p, ring_u32 + s * (kTps * kSlot * 4), bars_u32 + s * 8);
+      cursor_next<false>(cur, p, g);
     }
   }
-  int consumed = 0;  // stages consumed by this warp (same on all lanes)
+  int slot = 0;          // ring slot consumed next (same on all lanes)
+  uint32_t parity = 0;   // its mbarrier phase
 
   const int n = p.n;
   const int64_t plane = (int64_t)CT * n;  // floats per sample per state
@@ -286,7 +346,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) psf_chain_fwd_kernel(const Fus
 #pragma unroll
         for (int ch = 0; ch < CT; ++ch) {
           *reinterpret_cast<float4*>(Vs + ch * RB + (j - g.blk_start)) = pl[ch];
-          st_cg4(st0 + (int64_t)ch * n + j, pl[ch]);
+          st_cg4(st0 + ch * n + j, pl[ch]);
         }
       }
     }
@@ -311,58 +371,77 @@ __global__ void __launch_bounds__(kMaxThreads, 1) psf_chain_fwd_kernel(const Fus
         for (int ch = 0; ch < CT; ++ch) acc[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
 
         if (active) {
+          // one global-operand tap in flight: issued here, consumed after the next local taps
+          bool pend = false;
+          float4 pw = make_float4(1.f, 1.f, 1.f, 1.f);
+          float4 pv[CT];
+          if (mine && p.residual) {  // the residual V_0 rides the pending slot with weight 1
+#pragma unroll
+            for (int ch = 0; ch < CT; ++ch) pv[ch] = ld_cg4(st0 + ch * n + j);
+            pend = true;
+          }
+          const float* vown = Vs + (j - g.blk_start);
           for (int tg = 0; tg < g.ngroups; ++tg) {
-            const int s = consumed % kStages;
-            mbar_wait(smem_u32(&bars[s]), (uint32_t)((consumed / kStages) & 1));
-            const float* wst = ring + s * kTps * kSlot;
+            const int s = slot;
+            mbar_wait(bars_u32 + s * 8, parity);
+            const float* wst = ring + s * kTps * kSlot + 4 * g.lane;
             if (mine) {
+              if (tg == 0 && p.head) {
+                // taps with offsets 0,1,2,4 share the quads A = rows j..j+3 and Bq = rows j+4..j+7
+                const float4 w0 = lds4(wst), w1 = lds4(wst + kSlot), w2 = lds4(wst + 2 * kSlot),
+                             w3 = lds4(wst + 3 * kSlot);
+                const bool bq_local = (j + 8 <= g.blk_end);
+                const int jb = (j + 4 >= n) ? j + 4 - n : j + 4;
 #pragma unroll
-              for (int t = 0; t < kTps; ++t) {
-                const int k = tg * kTps + t;
-                if (k < p.L) {
-                  const float4 w4 = *reinterpret_cast<const float4*>(wst + t * kSlot + 4 * g.lane);
-                  const int o = p.offs.o[k];
-                  const int src = j + o;
-                  if ((o & 3) == 0) {
-                    if (src + 4 <= g.blk_end) {
-                      const float* vp = Vs + (src - g.blk_start);
+                for (int ch = 0; ch < CT; ++ch) {
+                  const float4 A = lds4(vown + ch * RB);
+                  const float4 Bq = bq_local ? lds4(vown + ch * RB + 4) : ld_cg4(prev + ch * n + jb);
+                  // row r: w0[r]*V[j+r] + w1[r]*V[j+r+1] + w2[r]*V[j+r+2] + w3[r]*V[j+r+4]
+                  fma4(acc[ch], w0, A);                                   // tap 0
+                  fma4(acc[ch], w3, Bq);                                  // tap 4
+                  fma2(acc[ch].x, acc[ch].y, w2.x, w2.y, A.z, A.w);       // tap 2, rows 0-1
+                  fma2(acc[ch].z, acc[ch].w, w2.z, w2.w, Bq.x, Bq.y);     // tap 2, rows 2-3
+                  acc[ch].x = fmaf(w1.x, A.y, acc[ch].x);                 // tap 1
+                  acc[ch].y = fmaf(w1.y, A.z, acc[ch].y);
+                  acc[ch].z = fmaf(w1.z, A.w, acc[ch].z);
+                  acc[ch].w = fmaf(w1.w, Bq.x, acc[ch].w);
+                }
+              } else {
 #pragma unroll
-                      for (int ch = 0; ch < CT; ++ch)
-                        fma4(acc[ch], w4, *reinterpret_cast<const float4*>(vp + ch * RB));
-                    } else {
-                      const int sw = src >= n ? src - n : src;
-                      const float* gp = prev + sw;
-                      float4 v[CT];
+                for (int t = 0; t < kTps; ++t) {
+                  const int i = tg * kTps + t;
+                  if (i < p.L) {
+                    const float4 w4 = lds4(wst + t * kSlot);
+                    const int o = p.ooffs.o[i];
+                    const int src = j + o;
+                    if ((o & 3) == 0) {
+                      if (src + 4 <= g.blk_end) {
+                        const float* vp = vown + o;
 #pragma unroll
-                      for (int ch = 0; ch < CT; ++ch) v[ch] = ld_cg4(gp + (int64_t)ch * n);
+                        for (int ch = 0; ch < CT; ++ch) fma4(acc[ch], w4, lds4(vp + ch * RB));
+                      } else {
+                        if (pend) {
 #pragma unroll
-                      for (int ch = 0; ch < CT; ++ch) fma4(acc[ch], w4, v[ch]);
-                    }
-                  } else {
-                    if (src + 4 <= g.blk_end) {
-                      const float* vp = Vs + (src - g.blk_start);
+                          for (int ch = 0; ch < CT; ++ch) fma4(acc[ch], pw, pv[ch]);
+                        }
+                        const float* gp = prev + (src >= n ? src - n : src);
+                        pw = w4;
 #pragma unroll
-                      for (int ch = 0; ch < CT; ++ch) {
-                        acc[ch].x = fmaf(w4.x, vp[ch * RB + 0], acc[ch].x);
-                        acc[ch].y = fmaf(w4.y, vp[ch * RB + 1], acc[ch].y);
-                        acc[ch].z = fmaf(w4.z, vp[ch * RB + 2], acc[ch].z);
-                        acc[ch].w = fmaf(w4.w, vp[ch * RB + 3], acc[ch].w);
+                        for (int ch = 0; ch < CT; ++ch) pv[ch] = ld_cg4(gp + ch * n);
+                        pend = true;
                       }
                     } else {
+                      // unaligned tap: the two aligned quads covering rows src..src+3, select in registers
+                      const int sh = o & 3;
+                      const int a = src - sh;
+                      const bool xl = (a + 4 <= g.blk_end), yl = (a + 8 <= g.blk_end);
+                      const int ax = a >= n ? a - n : a;
+                      const int ay = (a + 4 >= n) ? a + 4 - n : a + 4;
 #pragma unroll
-                      for (int r = 0; r < 4; ++r) {
-                        const int sr = src + r;
-                        const float wr = (r == 0) ? w4.x : (r == 1) ? w4.y : (r == 2) ? w4.z : w4.w;
-                        if (sr < g.blk_end) {
-                          const float* vp = Vs + (sr - g.blk_start);
-#pragma unroll
-                          for (int ch = 0; ch < CT; ++ch) f4at(acc[ch], r) = fmaf(wr, vp[ch * RB], f4at(acc[ch], r));
-                        } else {
-                          const float* gp = prev + (sr >= n ? sr - n : sr);
-#pragma unroll
-                          for (int ch = 0; ch < CT; ++ch)
-                            f4at(acc[ch], r) = fmaf(wr, ld_cg1(gp + (int64_t)ch * n), f4at(acc[ch], r));
-                        }
+                      for (int ch = 0; ch < CT; ++ch) {
+                        const float4 X = xl ? lds4(vown + (o - sh) + ch * RB) : ld_cg4(prev + ch * n + ax);
+                        const float4 Y = yl ? lds4(vown + (o - sh) + 4 + ch * RB) : ld_cg4(prev + ch * n + ay);
+                        fma4(acc[ch], w4, select_quad(X, Y, sh));
                       }
                     }
                   }
@@ -370,22 +449,18 @@ __global__ void __launch_bounds__(kMaxThreads, 1) psf_chain_fwd_kernel(const Fus
               }
             }
             __syncwarp();
-            ++consumed;
+            if (++slot == S) {
+              slot = 0;
+              parity ^= 1u;
+            }
             if (cur.valid) {  // refill the slot just drained
-              if (g.lane == 0) issue_stage(cur, p, g, ring + s * kTps * kSlot, smem_u32(&bars[s]));
-              cursor_next(cur, p, g);
-              ++issued;
+              if (g.lane == 0) issue_stage<false, kTps, kSlot>(cur, p, ring_u32 + s * (kTps * kSlot * 4), bars_u32 + s * 8);
+              cursor_next<false>(cur, p, g);
             }
           }
-          if (mine && p.residual) {
+          if (pend) {
 #pragma unroll
-            for (int ch = 0; ch < CT; ++ch) {
-              const float4 r4 = ld_cg4(st0 + (int64_t)ch * n + j);
-              acc[ch].x += r4.x;
-              acc[ch].y += r4.y;
-              acc[ch].z += r4.z;
-              acc[ch].w += r4.w;
-            }
+            for (int ch = 0; ch < CT; ++ch) fma4(acc[ch], pw, pv[ch]);
           }
         }
         __syncthreads();  // every read of this chunk's rows (by this chunk and all lower ones) is done
@@ -394,7 +469,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) psf_chain_fwd_kernel(const Fus
 #pragma unroll
             for (int ch = 0; ch < CT; ++ch) {
               *reinterpret_cast<float4*>(Vs + ch * RB + (j - g.blk_start)) = acc[ch];
-              st_cg4(next + (int64_t)ch * n + j, acc[ch]);
+              st_cg4(next + ch * n + j, acc[ch]);
             }
           } else {
             store_rows_natural(p.Vout + ((int64_t)b * n + j) * CT, acc);
@@ -410,61 +485,55 @@ __global__ void __launch_bounds__(kMaxThreads, 1) psf_chain_fwd_kernel(const Fus
         if (tile < g.ntiles && j < g.blk_end) {
           float4 pl[CT];
 #pragma unroll
-          for (int ch = 0; ch < CT; ++ch) pl[ch] = *reinterpret_cast<float4*>(Vs + ch * RB + (j - g.blk_start));
+          for (int ch = 0; ch < CT; ++ch) pl[ch] = lds4(Vs + ch * RB + (j - g.blk_start));
           store_rows_natural(p.Vout + ((int64_t)b * n + j) * CT, pl);
         }
       }
       cluster_sync_all();
     }
   }
-  (void)issued;
 }
 
 // ---------------------------------------------------------------------------------------------
 // Backward
 // ---------------------------------------------------------------------------------------------
+template <int kPlane>
 __global__ void __launch_bounds__(kMaxThreads, 1) psf_chain_bwd_kernel(const FusedParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int kTps = kTpsB, kSlot = kSlotB;
   WarpGeom g;
-  g.warp = threadIdx.x >> 5;
-  g.lane = threadIdx.x & 31;
-  g.nwarps = blockDim.x >> 5;
-  const int rank = blockIdx.x % p.P;
-  g.cid = blockIdx.x / p.P;
-  g.ncl = gridDim.x / p.P;
-  g.blk_start = min(p.n, rank * p.RB);
-  g.blk_end = min(p.n, g.blk_start + p.RB);
-  g.ntiles = (g.blk_end - g.blk_start + kTile - 1) / kTile;
-  g.nchunks = (g.ntiles + g.nwarps - 1) / g.nwarps;
-  g.ngroups = (p.L + kTps - 1) / kTps;
+  make_geom(g, p, kTps);
 
-  float* Gs = reinterpret_cast<float*>(smem_raw);  // [CT][RB]
-  const int RB = p.RB;
-  float* ring = Gs + CT * RB + (size_t)g.warp * kStages * kTps * kSlot;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Gs + CT * RB + (size_t)g.nwarps * kStages * kTps * kSlot) + g.warp * kStages;
+  float* Gs = reinterpret_cast<float*>(smem_raw);  // [CT][kPlane]
+  constexpr int RB = kPlane;
+  const int S = p.stages;
+  float* ring = Gs + CT * RB + (size_t)g.warp * S * kTps * kSlot;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Gs + CT * RB + (size_t)g.nwarps * S * kTps * kSlot) + g.warp * S;
 
+  const uint32_t ring_u32 = smem_u32(ring), bars_u32 = smem_u32(bars);
   if (g.lane == 0) {
-    for (int s = 0; s < kStages; ++s) mbar_init(smem_u32(&bars[s]), 1);
+    for (int s = 0; s < S; ++s) mbar_init(bars_u32 + s * 8, 1);
     fence_barrier_init();
   }
   __syncwarp();
 
-  WCursor<true> cur;
-  cursor_init(cur, p, g);
-  for (int s = 0; s < kStages; ++s) {
+  WCursor cur;
+  cursor_init<true>(cur, p, g);
+  for (int s = 0; s < S; ++s) {
     if (cur.valid) {
-      if (g.lane == 0) issue_stage(cur, p, g, ring + s * kTps * kSlot, smem_u32(&bars[s]));
-      cursor_next(cur, p, g);
+      if (g.lane == 0) issue_stage<true, kTps, kSlot>(cur, p, ring_u32 + s * (kTps * kSlot * 4), bars_u32 + s * 8);
+      cursor_next<true>(cur, p, g);
     }
   }
-  int consumed = 0;
+  int slot = 0;
+  uint32_t parity = 0;
 
   const int n = p.n;
   const int64_t plane = (int64_t)CT * n;
 
   for (int b = g.cid; b < p.B; b += g.ncl) {
-    float* gx0 = p.gx + (int64_t)b * plane;                    // exchange slot 0
-    float* gx1 = p.gx + ((int64_t)p.B + b) * plane;            // exchange slot 1
+    float* gx0 = p.gx + (int64_t)b * plane;          // exchange slot 0
+    float* gx1 = p.gx + ((int64_t)p.B + b) * plane;  // exchange slot 1
     float* racc = p.racc + (int64_t)b * plane;
     // ---- prologue: dOut block -> shared + exchange slot 0 ---------------------------------
     for (int c = 0; c < g.nchunks; ++c) {
@@ -476,7 +545,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) psf_chain_bwd_kernel(const Fus
 #pragma unroll
         for (int ch = 0; ch < CT; ++ch) {
           *reinterpret_cast<float4*>(Gs + ch * RB + (j - g.blk_start)) = pl[ch];
-          st_cg4(gx0 + (int64_t)ch * n + j, pl[ch]);
+          st_cg4(gx0 + ch * n + j, pl[ch]);
         }
       }
     }
@@ -499,39 +568,40 @@ __global__ void __launch_bounds__(kMaxThreads, 1) psf_chain_bwd_kernel(const Fus
         float4 acc[CT];
 #pragma unroll
         for (int ch = 0; ch < CT; ++ch) acc[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 rsum[CT];  // residual: racc so far, loaded before the barrier, used after it
 
         if (active) {
           float4 vown[CT];
           if (mine) {
 #pragma unroll
-            for (int ch = 0; ch < CT; ++ch) vown[ch] = ld_cg4(vprev + (int64_t)ch * n + j);
+            for (int ch = 0; ch < CT; ++ch) vown[ch] = ld_cg4(vprev + ch * n + j);
           }
+          const float* gown = Gs + (j - g.blk_start);
           for (int tg = 0; tg < g.ngroups; ++tg) {
-            const int s = consumed % kStages;
-            mbar_wait(smem_u32(&bars[s]), (uint32_t)((consumed / kStages) & 1));
-            const float* wst = ring + s * kTps * kSlot;
+            const int s = slot;
+            mbar_wait(bars_u32 + s * 8, parity);
+            const float* wst = ring + s * kTps * kSlot + 4 * g.lane;
             if (mine) {
 #pragma unroll
               for (int t = 0; t < kTps; ++t) {
-                const int k = tg * kTps + t;
-                if (k < p.L) {
-                  const int o = p.offs.o[k];
+                const int i = tg * kTps + t;
+                if (i < p.L) {
+                  const int o = p.ooffs.o[i];
                   const int src = j - o;  // first source row (may be negative: cyclic)
-                  float* dwk = dwbase + (int64_t)k * p.sWt;
+                  float* dwk = dwbase + p.tapoff[i];
                   if ((o & 3) == 0) {
-                    const float4 w4 = *reinterpret_cast<const float4*>(wst + t * kSlot + 4 * g.lane);
+                    const float4 w4 = lds4(wst + t * kSlot);
                     float4 gv[CT];
                     int sw;
                     if (src >= g.blk_start) {
                       sw = src;
-                      const float* gp = Gs + (src - g.blk_start);
 #pragma unroll
-                      for (int ch = 0; ch < CT; ++ch) gv[ch] = *reinterpret_cast<const float4*>(gp + ch * RB);
+                      for (int ch = 0; ch < CT; ++ch) gv[ch] = lds4(gown - o + ch * RB);
                     } else {
                       sw = src < 0 ? src + n : src;
                       const float* gp = gcur + sw;
 #pragma unroll
-                      for (int ch = 0; ch < CT; ++ch) gv[ch] = ld_cg4(gp + (int64_t)ch * n);
+                      for (int ch = 0; ch < CT; ++ch) gv[ch] = ld_cg4(gp + ch * n);
                     }
                     float4 dw = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -541,79 +611,71 @@ __global__ void __launch_bounds__(kMaxThreads, 1) psf_chain_bwd_kernel(const Fus
                     }
                     st_cs4(dwk + sw, dw);
                   } else {
-                    // unaligned tap: 32-bit accesses, per-row local/remote decision
-                    int s0 = row0 - o;
-                    if (s0 < 0) s0 += n;
-                    const int lead = s0 & 3;
-                    const float* wrow = wst + t * kSlot + lead + 4 * g.lane;
+                    // unaligned tap: aligned quads X = rows a..a+3, Y = rows a+4..a+7 cover src..src+3
+                    const int sh = (4 - (o & 3)) & 3;  // src mod 4 (j is a multiple of 4)
+                    const int a = src - sh;
+                    const bool xl = (a >= g.blk_start), yl = (a + 4 >= g.blk_start);
+                    const int ax = a < 0 ? a + n : a;
+                    const int ay = (a + 4 < 0) ? a + 4 + n : a + 4;
+                    const float4 w4 = select_quad(lds4(wst + t * kSlot), lds4(wst + t * kSlot + 4), sh);
+                    float4 dw = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                      const int sr = src + r;
-                      const float wr = wrow[r];
-                      float dwr = 0.f;
-                      int swr;
-                      if (sr >= g.blk_start) {
-                        swr = sr;
-                        const float* gp = Gs + (sr - g.blk_start);
-#pragma unroll
-                        for (int ch = 0; ch < CT; ++ch) {
-                          const float gvv = gp[ch * RB];
-                          f4at(acc[ch], r) = fmaf(wr, gvv, f4at(acc[ch], r));
-                          dwr = fmaf(gvv, f4at(vown[ch], r), dwr);
-                        }
-                      } else {
-                        swr = sr < 0 ? sr + n : sr;
-                        const float* gp = gcur + swr;
-#pragma unroll
-                        for (int ch = 0; ch < CT; ++ch) {
-                          const float gvv = ld_cg1(gp + (int64_t)ch * n);
-                          f4at(acc[ch], r) = fmaf(wr, gvv, f4at(acc[ch], r));
-                          dwr = fmaf(gvv, f4at(vown[ch], r), dwr);
-                        }
-                      }
-                      __stcs(dwk + swr, dwr);
+                    for (int ch = 0; ch < CT; ++ch) {
+                      const float4 X = xl ? lds4(gown - o - sh + ch * RB) : ld_cg4(gcur + ch * n + ax);
+                      const float4 Y = yl ? lds4(gown - o - sh + 4 + ch * RB) : ld_cg4(gcur + ch * n + ay);
+                      const float4 gq = select_quad(X, Y, sh);
+                      fma4(acc[ch], w4, gq);
+                      fma4(dw, gq, vown[ch]);
                     }
+                    // rows src..src+3 (cyclic) of dW_k: not 16 B aligned -> four scalar stores
+                    int r0 = src < 0 ? src + n : src;
+                    __stcs(dwk + r0, dw.x);
+                    r0 = (r0 + 1 == n) ? 0 : r0 + 1;
+                    __stcs(dwk + r0, dw.y);
+                    r0 = (r0 + 1 == n) ? 0 : r0 + 1;
+                    __stcs(dwk + r0, dw.z);
+                    r0 = (r0 + 1 == n) ? 0 : r0 + 1;
+                    __stcs(dwk + r0, dw.w);
                   }
                 }
               }
             }
             __syncwarp();
-            ++consumed;
+            if (++slot == S) {
+              slot = 0;
+              parity ^= 1u;
+            }
             if (cur.valid) {
-              if (g.lane == 0) issue_stage(cur, p, g, ring + s * kTps * kSlot, smem_u32(&bars[s]));
-              cursor_next(cur, p, g);
+              if (g.lane == 0) issue_stage<true, kTps, kSlot>(cur, p, ring_u32 + s * (kTps * kSlot * 4), bars_u32 + s * 8);
+              cursor_next<true>(cur, p, g);
             }
           }
-          // residual: dV0 also receives G_m of every factor (V_m = W_m V_{m-1} + V_0)
-          if (mine && p.residual) {
+          // residual: fetch the running sum now, its latency hides behind the barrier
+          if (mine && p.residual && m != p.n_W) {
 #pragma unroll
-            for (int ch = 0; ch < CT; ++ch) {
-              float4 own = *reinterpret_cast<const float4*>(Gs + ch * RB + (j - g.blk_start));
-              if (m != p.n_W) {
-                const float4 r4 = ld_cg4(racc + (int64_t)ch * n + j);
-                own.x += r4.x;
-                own.y += r4.y;
-                own.z += r4.z;
-                own.w += r4.w;
-              }
-              if (!last) {
-                st_cg4(racc + (int64_t)ch * n + j, own);
-              } else {
-                acc[ch].x += own.x;
-                acc[ch].y += own.y;
-                acc[ch].z += own.z;
-                acc[ch].w += own.w;
-              }
-            }
+            for (int ch = 0; ch < CT; ++ch) rsum[ch] = ld_cg4(racc + ch * n + j);
           }
         }
         __syncthreads();
         if (mine) {
+          // residual: dV0 also receives G_m of every factor (V_m = W_m V_{m-1} + V_0)
+          if (p.residual) {
+#pragma unroll
+            for (int ch = 0; ch < CT; ++ch) {
+              float4 own = lds4(Gs + ch * RB + (j - g.blk_start));
+              if (m != p.n_W) add4(own, rsum[ch]);
+              if (!last) {
+                st_cg4(racc + ch * n + j, own);
+              } else {
+                add4(acc[ch], own);
+              }
+            }
+          }
           if (!last) {
 #pragma unroll
             for (int ch = 0; ch < CT; ++ch) {
               *reinterpret_cast<float4*>(Gs + ch * RB + (j - g.blk_start)) = acc[ch];
-              st_cg4(gnext + (int64_t)ch * n + j, acc[ch]);
+              st_cg4(gnext + ch * n + j, acc[ch]);
             }
           } else {
             store_rows_natural(p.Vout + ((int64_t)b * n + j) * CT, acc);
@@ -629,7 +691,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) psf_chain_bwd_kernel(const Fus
         if (tile < g.ntiles && j < g.blk_end) {
           float4 pl[CT];
 #pragma unroll
-          for (int ch = 0; ch < CT; ++ch) pl[ch] = *reinterpret_cast<float4*>(Gs + ch * RB + (j - g.blk_start));
+          for (int ch = 0; ch < CT; ++ch) pl[ch] = lds4(Gs + ch * RB + (j - g.blk_start));
           store_rows_natural(p.Vout + ((int64_t)b * n + j) * CT, pl);
         }
       }
@@ -641,71 +703,54 @@ __global__ void __launch_bounds__(kMaxThreads, 1) psf_chain_bwd_kernel(const Fus
 // ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
-int smem_bytes_for(int RB, int threads) {
+int plane_for(int RB) { return RB <= 512 ? 512 : (RB <= 2048 ? 2048 : 4096); }
+
+int smem_bytes_for(int RB, int threads, int stages, bool backward) {
   const int nwarps = threads / 32;
-  return CT * RB * 4 + nwarps * kStages * kTps * kSlot * 4 + nwarps * kStages * 8;
+  const int ring = backward ? stages * kTpsB * kSlotB : stages * kTpsF * kSlotF;
+  return CT * plane_for(RB) * 4 + nwarps * ring * 4 + nwarps * stages * 8;
 }
 
-int g_attr_done_fwd = 0, g_attr_done_bwd = 0;
-
-int launch(const void* kernel, const FusedParams& fp, const PsfFusedPlan& plan, cudaStream_t st) {
-  cudaLaunchConfig_t cfg = {};
-  const int clusters = plan.resident < fp.B ? plan.resident : fp.B;
-  cfg.gridDim = dim3((unsigned)(clusters * plan.cluster), 1, 1);
-  cfg.blockDim = dim3((unsigned)plan.threads, 1, 1);
-  cfg.dynamicSmemBytes = (size_t)plan.smem_bytes;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)plan.cluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  void* args[] = {(void*)&fp};
-  return (int)cudaLaunchKernelExC(&cfg, kernel, args);
+const void* fwd_kernel_for(int RB) {
+  switch (plane_for(RB)) {
+    case 512: return (const void*)psf_chain_fwd_kernel<512>;
+    case 2048: return (const void*)psf_chain_fwd_kernel<2048>;
+    default: return (const void*)psf_chain_fwd_kernel<4096>;
+  }
+}
+const void* bwd_kernel_for(int RB) {
+  switch (plane_for(RB)) {
+    case 512: return (const void*)psf_chain_bwd_kernel<512>;
+    case 2048: return (const void*)psf_chain_bwd_kernel<2048>;
+    default: return (const void*)psf_chain_bwd_kernel<4096>;
+  }
 }
 
-}  // namespace
+int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  if (v == nullptr || *v == 0) return dflt;
+  const int x = std::atoi(v);
+  return x > 0 ? x : dflt;
+}
 
-int psf_fused_plan(const PsfChainArgs& a, PsfFusedPlan* plan) {
-  if (a.C != CT || a.n < 4 || (a.n & 3) || a.n > 8 * (int64_t)kMaxBlockRows || a.L < 1 || a.L > PSF_MAX_TAPS ||
-      a.n_W < 0 || a.B < 1 || a.B > (1 << 20))
-    return PSF_ERR_UNSUPPORTED;
-  if (a.ws.row != 1 || (a.ws.factor & 3) || (a.ws.sample & 3) || (a.ws.tap & 3)) return PSF_ERR_UNSUPPORTED;
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) != cudaSuccess) return PSF_ERR_UNSUPPORTED;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int P = 1;
-  while ((a.n + P - 1) / P > kMaxBlockRows) P *= 2;
-  // spread small batches over more SMs while a CTA still has at least 4 warp tiles
-  while (P < 8 && a.B * P * 2 <= sms && (a.n + 2 * P - 1) / (2 * P) >= 4 * kTile) P *= 2;
-  const int per = (int)((a.n + P - 1) / P);
-  const int RB = (per + 3) & ~3;
-  int threads = ((RB + kTile - 1) / kTile) * 32;
-  if (threads > kMaxThreads) threads = kMaxThreads;
-  plan->cluster = P;
-  plan->rows_per_cta = RB;
-  plan->threads = threads;
-  plan->smem_bytes = smem_bytes_for(RB, threads);
+bool g_attr_done = false;
 
-  if (!g_attr_done_fwd) {
-    if (cudaFuncSetAttribute((const void*)psf_chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             227 * 1024) != cudaSuccess)
-      return PSF_ERR_UNSUPPORTED;
-    g_attr_done_fwd = 1;
-  }
-  if (!g_attr_done_bwd) {
-    if (cudaFuncSetAttribute((const void*)psf_chain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             227 * 1024) != cudaSuccess)
-      return PSF_ERR_UNSUPPORTED;
-    g_attr_done_bwd = 1;
-  }
-  // how many clusters of this shape are resident at once (the kernels are persistent over samples)
+struct OccCache {
+  int P, threads, smem, backward, clusters;
+  const void* kernel;
+};
+OccCache g_occ[16];
+int g_occ_n = 0;
+
+int resident_clusters(const void* kernel, int P, int threads, int smem, int backward, int sms) {
+  for (int i = 0; i < g_occ_n; ++i)
+    if (g_occ[i].P == P && g_occ[i].threads == threads && g_occ[i].smem == smem && g_occ[i].backward == backward &&
+        g_occ[i].kernel == kernel)
+      return g_occ[i].clusters;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(P * sms), 1, 1);
+  cfg.gridDim = dim3((unsigned)(P * sms * 2), 1, 1);
   cfg.blockDim = dim3((unsigned)threads, 1, 1);
-  cfg.dynamicSmemBytes = (size_t)plan->smem_bytes;
+  cfg.dynamicSmemBytes = (size_t)smem;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)P;
@@ -714,12 +759,152 @@ int psf_fused_plan(const PsfChainArgs& a, PsfFusedPlan* plan) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int nclusters = 0;
-  if (cudaOccupancyMaxActiveClusters(&nclusters, (const void*)psf_chain_bwd_kernel, &cfg) != cudaSuccess ||
-      nclusters < 1) {
+  if (cudaOccupancyMaxActiveClusters(&nclusters, kernel, &cfg) != cudaSuccess || nclusters < 1) {
     cudaGetLastError();
-    return PSF_ERR_UNSUPPORTED;
+    return 0;
   }
-  plan->resident = nclusters;
+  if (g_occ_n < 16) g_occ[g_occ_n++] = {P, threads, smem, backward, nclusters, kernel};
+  return nclusters;
+}
+
+// Tap visiting order.  Forward: the {0,1,2,4} head first (if present), then big offsets interleaved
+// 1:3 with small ones so every (possibly remote) big tap is followed by local work.  Backward: natural.
+void make_order(const PsfChainArgs& a, bool backward, PsfOffsets* order, int* head) {
+  const int L = a.L;
+  *head = 0;
+  for (int i = 0; i < PSF_MAX_TAPS; ++i) order->o[i] = i < L ? i : 0;
+  if (backward) return;
+  bool used[PSF_MAX_TAPS] = {false};
+  int pos = 0;
+  const int want[4] = {0, 1, 2, 4};
+  int hk[4] = {-1, -1, -1, -1};
+  for (int w = 0; w < 4; ++w)
+    for (int k = 0; k < L; ++k)
+      if (hk[w] < 0 && !used[k] && a.offs.o[k] == want[w]) {
+        hk[w] = k;
+        used[k] = true;
+      }
+  if (hk[0] >= 0 && hk[1] >= 0 && hk[2] >= 0 && hk[3] >= 0 && a.n >= 8) {
+    *head = 1;
+    for (int w = 0; w < 4; ++w) order->o[pos++] = hk[w];
+  } else {
+    for (int k = 0; k < L; ++k) used[k] = false;
+  }
+  int rest[PSF_MAX_TAPS], nr = 0;
+  for (int k = 0; k < L; ++k)
+    if (!used[k]) rest[nr++] = k;
+  for (int i = 1; i < nr; ++i) {  // insertion sort by offset (stable)
+    const int k = rest[i];
+    int q = i - 1;
+    while (q >= 0 && a.offs.o[rest[q]] > a.offs.o[k]) {
+      rest[q + 1] = rest[q];
+      --q;
+    }
+    rest[q + 1] = k;
+  }
+  const int nb = (nr + 3) / 4;
+  int lo = 0, hi = nr - 1, bigs = 0;
+  while (lo <= hi) {
+    if (bigs < nb) {
+      order->o[pos++] = rest[hi--];
+      ++bigs;
+    }
+    for (int q = 0; q < 3 && lo <= hi; ++q) order->o[pos++] = rest[lo++];
+  }
+}
+
+int launch(const void* kernel, const FusedParams& fp, int P, int threads, int smem, int resident, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  const int clusters = resident < fp.B ? resident : fp.B;
+  cfg.gridDim = dim3((unsigned)(clusters * P), 1, 1);
+  cfg.blockDim = dim3((unsigned)threads, 1, 1);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)P;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  void* args[] = {(void*)&fp};
+  return (int)cudaLaunchKernelExC(&cfg, kernel, args);
+}
+
+void fill_common(FusedParams& fp, const PsfChainArgs& a, const PsfFusedPlan& plan, bool backward) {
+  fp.sWf = a.ws.factor;
+  fp.sWb = a.ws.sample;
+  fp.sWt = a.ws.tap;
+  fp.B = (int)a.B;
+  fp.n = (int)a.n;
+  fp.n_W = a.n_W;
+  fp.L = a.L;
+  fp.residual = a.residual;
+  fp.P = plan.cluster;
+  fp.RB = plan.rows_per_cta;
+  fp.stages = plan.stages;
+  fp.offs = a.offs;
+  make_order(a, backward, &fp.order, &fp.head);
+  for (int i = 0; i < PSF_MAX_TAPS; ++i) {
+    fp.ooffs.o[i] = a.offs.o[fp.order.o[i]];
+    fp.tapoff[i] = (long long)fp.order.o[i] * a.ws.tap;
+  }
+}
+
+}  // namespace
+
+int psf_fused_plan(const PsfChainArgs& a, PsfFusedPlan* plan) {
+  if (a.C != CT || a.n < 4 || (a.n & 3) || a.L < 1 || a.L > PSF_MAX_TAPS || a.n_W < 0 || a.B < 1 ||
+      a.B > (1 << 20))
+    return PSF_ERR_UNSUPPORTED;
+  if (a.ws.row != 1 || (a.ws.factor & 3) || (a.ws.sample & 3) || (a.ws.tap & 3)) return PSF_ERR_UNSUPPORTED;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess) return PSF_ERR_UNSUPPORTED;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // block rows: 2048 (64 KB, two CTAs per SM) unless that needs more than 8 CTAs per sample
+  int max_rows = env_int("PSF_FUSED_MAX_ROWS", 2048);
+  int max_threads = env_int("PSF_FUSED_MAX_THREADS", 256);
+  if (max_threads > kMaxThreads) max_threads = kMaxThreads;
+  max_threads &= ~31;
+  if (max_threads < 32) max_threads = 32;
+  int P = 1;
+  while ((a.n + P - 1) / P > max_rows && P < 8) P *= 2;
+  if ((a.n + P - 1) / P > max_rows) {
+    max_rows = 4096;
+    max_threads = kMaxThreads;
+    if ((a.n + P - 1) / P > max_rows) return PSF_ERR_UNSUPPORTED;
+  }
+  // spread small batches over more SMs while a CTA keeps at least 4 warp tiles
+  while (P < 8 && a.B * P * 2 <= 2 * sms && (a.n + 2 * P - 1) / (2 * P) >= 4 * kTile) P *= 2;
+  const int per = (int)((a.n + P - 1) / P);
+  const int RB = (per + 3) & ~3;
+  int threads = ((RB + kTile - 1) / kTile) * 32;
+  if (threads > max_threads) threads = max_threads;
+  plan->cluster = P;
+  plan->rows_per_cta = RB;
+  plan->threads = threads;
+  int stages = env_int("PSF_FUSED_STAGES", 3);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) stages = 2;
+  while (stages > 2 && smem_bytes_for(RB, threads, stages, true) > 227 * 1024) --stages;
+  if (smem_bytes_for(RB, threads, stages, true) > 227 * 1024) return PSF_ERR_UNSUPPORTED;
+  plan->stages = stages;
+  plan->smem_bytes = smem_bytes_for(RB, threads, stages, false);
+  plan->smem_bytes_bwd = smem_bytes_for(RB, threads, stages, true);
+
+  if (!g_attr_done) {
+    const int planes[3] = {512, 2048, 4096};
+    for (int q = 0; q < 3; ++q)
+      if (cudaFuncSetAttribute(fwd_kernel_for(planes[q]), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+              cudaSuccess ||
+          cudaFuncSetAttribute(bwd_kernel_for(planes[q]), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+              cudaSuccess)
+        return PSF_ERR_UNSUPPORTED;
+    g_attr_done = true;
+  }
+  plan->resident = resident_clusters(fwd_kernel_for(RB), P, threads, plan->smem_bytes, 0, sms);
+  plan->resident_bwd = resident_clusters(bwd_kernel_for(RB), P, threads, plan->smem_bytes_bwd, 1, sms);
+  if (plan->resident < 1 || plan->resident_bwd < 1) return PSF_ERR_UNSUPPORTED;
   return PSF_OK;
 }
 
@@ -740,19 +925,9 @@ int psf_fused_chain_fwd(const PsfChainArgs& a, const float* W, const float* V0, 
   fp.Vin = V0;
   fp.Vout = out;
   fp.states = ws;
-  fp.sWf = a.ws.factor;
-  fp.sWb = a.ws.sample;
-  fp.sWt = a.ws.tap;
-  fp.B = (int)a.B;
-  fp.n = (int)a.n;
-  fp.n_W = a.n_W;
-  fp.L = a.L;
-  fp.residual = a.residual;
   fp.save_states = save_states;
-  fp.P = plan.cluster;
-  fp.RB = plan.rows_per_cta;
-  fp.offs = a.offs;
-  return launch((const void*)psf_chain_fwd_kernel, fp, plan, st);
+  fill_common(fp, a, plan, false);
+  return launch(fwd_kernel_for(plan.rows_per_cta), fp, plan.cluster, plan.threads, plan.smem_bytes, plan.resident, st);
 }
 
 int psf_fused_chain_bwd(const PsfChainArgs& a, const float* W, const float* dOut, float* dW, float* dV0, float* ws,
@@ -769,17 +944,8 @@ int psf_fused_chain_bwd(const PsfChainArgs& a, const float* W, const float* dOut
   fp.states = ws;
   fp.gx = ws + (int64_t)a.n_W * S;
   fp.racc = fp.gx + 2 * S;
-  fp.sWf = a.ws.factor;
-  fp.sWb = a.ws.sample;
-  fp.sWt = a.ws.tap;
-  fp.B = (int)a.B;
-  fp.n = (int)a.n;
-  fp.n_W = a.n_W;
-  fp.L = a.L;
-  fp.residual = a.residual;
   fp.save_states = 1;
-  fp.P = plan.cluster;
-  fp.RB = plan.rows_per_cta;
-  fp.offs = a.offs;
-  return launch((const void*)psf_chain_bwd_kernel, fp, plan, st);
+  fill_common(fp, a, plan, true);
+  return launch(bwd_kernel_for(plan.rows_per_cta), fp, plan.cluster, plan.threads, plan.smem_bytes_bwd,
+                plan.resident_bwd, st);
 }

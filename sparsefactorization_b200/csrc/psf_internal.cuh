@@ -53,8 +53,11 @@ struct PsfFusedPlan {
   int cluster;        // CTAs per sample
   int rows_per_cta;   // RB, multiple of 4
   int threads;        // per CTA
-  int smem_bytes;     // dynamic shared memory
-  int resident;       // clusters that fit on the device at once
+  int smem_bytes;     // dynamic shared memory, forward kernel
+  int resident;       // clusters that fit on the device at once, forward kernel
+  int smem_bytes_bwd; // same for the backward kernel (different W ring geometry)
+  int resident_bwd;
+  int stages;         // W ring depth per warp
 };
 int psf_fused_plan(const PsfChainArgs& a, PsfFusedPlan* plan);   // PSF_OK or PSF_ERR_UNSUPPORTED
 bool psf_fused_buffers_ok(const PsfChainArgs& a, const void* W, const void* p1, const void* p2, const void* ws);
