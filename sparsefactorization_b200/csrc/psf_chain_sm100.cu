@@ -1,34 +1,33 @@
 // Fused chord-factor chain for sm_100a (B200): forward and backward, fp32, C = 8 channels.
 //
 // One thread-block CLUSTER owns one sample.  CTA q of a P-CTA cluster owns the contiguous row
-// block [q*RB, (q+1)*RB) for ALL channels and keeps it in shared memory, channel-major
-// ([C][RB] fp32), across all n_W factors.  Facts the design is built on:
-//   * chord links only point forward (row i reads rows i+o_k, o_k >= 0), so a block can be
-//     updated IN PLACE by an ascending sweep over 128-row warp tiles (descending for the
-//     backward pass, whose links point backward): once a tile has been read by itself and by
-//     every lower tile, nobody inside the CTA needs its old value again.  No ping-pong buffer,
-//     so a 2048-row block costs 64 KB and two CTAs (of different samples) share an SM: while one
-//     waits at a barrier the other computes.
-//   * operands that fall outside the CTA's block (big taps, the halo of small taps, the cyclic
-//     wrap) are read from the previous state in global memory.  That state was written by the
-//     sibling CTAs a few microseconds earlier and is L2 resident; a hardware cluster barrier
-//     (release/acquire) per factor orders the exchange.  The same buffers are the saved
-//     states V_0..V_{n_W-1} the backward pass needs, so training pays nothing extra for it.
-//   * W is streamed exactly once: tap-major ([..][tap][row], row stride 1) so that the 128 rows
-//     of a warp tile are one contiguous 512 B run per tap.  Lane 0 of every warp prefetches its
-//     own runs with cp.async.bulk (TMA, 1-D) into a private 3-stage ring guarded by mbarriers;
-//     no producer warp, no cross-warp coupling, chord offsets are arithmetic (no COO gathers).
-//   * every thread owns 4 consecutive rows x 8 channels: all shared/global operand accesses
-//     are 128-bit and bank-conflict free (consecutive lanes -> consecutive 16 B).  Taps whose
-//     offset is not a multiple of 4 read the two aligned quads that cover them and select in
-//     registers; in the forward pass taps {0,1,2,4} share the same two quads (13 instead of 15
-//     operand loads per row group and channel).
-//   * global (remote / residual) operand loads are issued one tap group ahead and consumed after
-//     the following local taps ("pending" slot); taps are visited big-offset-first, interleaved
-//     with small ones, so that every remote tap has local work to hide behind.
-//   * backward (output-stationary at row j):  one shifted read of G_m[j-o_k,:] feeds both
-//     dV_{m-1}[j,:] += W_m[j-o_k,k] * G_m[j-o_k,:]  and  dW_m[j-o_k,k] = <G_m[j-o_k,:], V_{m-1}[j,:]>,
-//     all C channels live in one thread so dW needs no cross-CTA reduction and is written once.
+// block [q*RB, (q+1)*RB) for ALL channels.  Structure of one CTA:
+//
+//   * STATE CACHE.  The current state of the block (V_{m-1} forward, G_m backward) sits in shared
+//     memory, channel-major [8][plane] fp32 (64 KB for 2048 rows), and is READ-ONLY during a factor.
+//     Every new state is written to global memory (it is L2 resident; forward states double as the
+//     saved V_0..V_{n_W-1} of the backward pass), and at the factor boundary the CTA pulls its own
+//     block back into shared memory with eight 8 KB TMA bulk copies.  No in-place hazard, so no
+//     barrier inside a factor; two CTAs (different samples) share an SM and cover each other's
+//     factor-boundary latency.
+//   * EXCHANGE.  Operands outside the CTA's block (big taps, halo of small taps, cyclic wrap) are
+//     read straight from the previous state in global memory (written by the sibling CTAs one
+//     factor earlier); one hardware cluster barrier (release/acquire) per factor orders it.
+//   * W STREAM.  W is read exactly once, tap-major ([..][tap][row], row stride 1): the rows a pass
+//     covers (consumer warps x 128) are one contiguous run per tap.  A dedicated producer warp
+//     issues cp.async.bulk (TMA 1-D, up to 4 KB each) into a CTA-shared ring of stages guarded by
+//     full/empty mbarriers; consumer warps never touch pointers into W.  Chord offsets are
+//     arithmetic, there are no COO index gathers anywhere.
+//   * MATH.  Every consumer thread owns 4 consecutive rows x 8 channels: all shared/global
+//     operand accesses are 128-bit and bank-conflict free, FMAs are packed fma.rn.f32x2.  Taps
+//     whose offset is not a multiple of 4 read the two aligned quads that cover them; in the
+//     forward pass taps {0,1,2,4} share the same two quads (13 instead of 15 operand loads per
+//     row group and channel).  Global operand loads ride a one-deep "pending" slot so their
+//     latency hides behind the following local taps; taps are visited big-offset-first,
+//     interleaved 1:3 with small ones.
+//   * BACKWARD (output-stationary at row j):  one shifted read of G_m[j-o_k,:] feeds both
+//     dV_{m-1}[j,:] += W_m[j-o_k,k] * G_m[j-o_k,:]  and  dW_m[j-o_k,k] = <G_m[j-o_k,:], V_{m-1}[j,:]>;
+//     all 8 channels live in one thread, so dW needs no cross-CTA reduction and is written once.
 //
 // Reference semantics: SyntheticExperiments/psf.py:167-188 (loop + residual), spmul_cuda.cu:24,
 // :79-80, :105-108 (per-factor formulas).
@@ -38,15 +37,17 @@
 
 namespace {
 
-constexpr int CT = 8;        // channels held per thread == C of the fast path
-constexpr int kTile = 128;   // rows per warp tile (32 lanes x 4 rows)
-constexpr int kMaxStages = 8; // W ring depth per warp is a launch parameter (<= 8)
-constexpr int kMaxThreads = 512;
+constexpr int CT = 8;          // channels held per thread == C of the fast path
+constexpr int kTile = 128;     // rows per warp tile (32 lanes x 4 rows)
+constexpr int kMaxCW = 8;      // consumer warps per CTA
+constexpr int kMaxStages = 8;  // W ring depth is a launch parameter
+constexpr int kMaxThreads = kMaxCW * 32;
 
-// ring geometry: forward stages 4 taps (the {0,1,2,4} head group is one stage) of exactly one tile;
-// backward stages 3 taps with 8 spare floats (shifted, 16 B aligned source windows).
-constexpr int kTpsF = 4, kSlotF = kTile;
-constexpr int kTpsB = 3, kSlotB = kTile + 8;
+// ring geometry: forward stages 4 taps (the {0,1,2,4} head group is one stage); backward stages
+// 3 taps whose per-tap windows carry 8 spare floats (16 B aligned, shifted source windows).
+constexpr int kTpsF = 4;
+constexpr int kTpsB = 3;
+constexpr int kPadB = 8;
 
 struct FusedParams {
   const float* W;
@@ -56,15 +57,16 @@ struct FusedParams {
   float* states;      // channel-major [slots][B][8][n]
   float* gx;          // bwd exchange  [2][B][8][n]
   float* racc;        // bwd residual accumulator [B][8][n]
-  int64_t sWf, sWb, sWt;
+  long long sWf, sWb;
   int B, n, n_W, L, residual, save_states;
   int P, RB;
-  int head;           // fwd: order[0..3] are the taps with offsets 0,1,2,4
-  int stages;         // W ring depth per warp
-  PsfOffsets offs;    // offset of tap k (mod n)
-  PsfOffsets order;   // order[i] = tap visited i-th
-  PsfOffsets ooffs;   // ooffs[i] = offs[order[i]]
-  long long tapoff[PSF_MAX_TAPS];  // order[i] * sWt (elements)
+  int head;           // fwd: visits 0..3 are the taps with offsets 0,1,2,4
+  int stages;         // W ring depth
+  int ncw;            // warps per CTA (warp 0 / lane 0 also streams W)
+  int dbg;            // timing experiments only (PSF_FUSED_DEBUG): 1 no state stores, 2 no cluster barrier,
+                      // 4 all taps local, 8 no W stream, 16 no state refresh, 32 no residual
+  PsfOffsets ooffs;   // ooffs[i] = offset (mod n) of the tap visited i-th
+  long long tapoff[PSF_MAX_TAPS];  // element offset of that tap's plane inside a factor (tap * sWt)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -77,6 +79,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
@@ -99,19 +104,33 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint3
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  asm volatile("fence.proxy.async;" ::: "memory");
 }
+// generic-proxy writes (st.global) -> later async-proxy reads (TMA) of the same bytes
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // Hardware cluster barrier; release/acquire at cluster scope orders the global-memory exchange.
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n"
-               "barrier.cluster.wait.acquire.aligned;\n" ::
-                   : "memory");
+__device__ __forceinline__ void cluster_arrive() {
+  asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait() {
+  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ void consumer_bar_sync(int nthreads) {
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
 }
 
 __device__ __forceinline__ float4 ld_cg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st_cg4(float* p, float4 v) { __stcg(reinterpret_cast<float4*>(p), v); }
 __device__ __forceinline__ void st_cs4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// same, but the compiler may not narrow it to the lanes that are used (narrow loads at a 16 B lane
+// stride are bank conflicted)
+__device__ __forceinline__ float4 lds4_full(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(smem_u32(p)));
+  return v;
+}
 
 // acc += a * b on 4 lanes as two packed fma.rn.f32x2 (FFMA2 on sm_100): half the FMA issue slots
 __device__ __forceinline__ void fma4(float4& acc, const float4& a, const float4& b) {
@@ -172,324 +191,394 @@ __device__ __forceinline__ void store_rows_natural(float* __restrict__ base, con
 }
 
 // ---------------------------------------------------------------------------------------------
-// Per-warp W prefetch cursor.  The issue order must equal the consume order:
-//   for sample b (this cluster's samples) / factor m / chunk c (tiles of this warp) / tap group tg.
-// kBackward: m and c run downwards, and the staged rows are shifted by -o_k.
+// CTA geometry shared by producer and consumers
 // ---------------------------------------------------------------------------------------------
-struct WCursor {
-  int b, m, c, tg;
-  bool valid;
-  int row0, rw;        // first row / rows of the tile being staged
-  const float* wptr;   // W + (m-1)*sWf + b*sWb (+ row0 in the forward pass)
-};
-
-struct WarpGeom {
-  int warp, lane, nwarps;
+struct Geom {
+  int warp, lane, ncw;
   int blk_start, blk_end;  // rows of this CTA
   int ntiles;              // 128-row tiles in the block
-  int nchunks;             // ceil(ntiles / nwarps)
+  int npass;               // ceil(ntiles / ncw): a pass = one tile per consumer warp
   int ngroups;             // ceil(L / taps per stage)
   int cid, ncl;            // cluster id, number of clusters
+  int prows;               // rows covered by a full pass (ncw * 128)
 };
 
-__device__ __forceinline__ void make_geom(WarpGeom& g, const FusedParams& p, int tps) {
+__device__ __forceinline__ void make_geom(Geom& g, const FusedParams& p, int tps) {
   g.warp = threadIdx.x >> 5;
   g.lane = threadIdx.x & 31;
-  g.nwarps = blockDim.x >> 5;
+  g.ncw = p.ncw;
   const int rank = blockIdx.x % p.P;
   g.cid = blockIdx.x / p.P;
   g.ncl = gridDim.x / p.P;
   g.blk_start = min(p.n, rank * p.RB);
   g.blk_end = min(p.n, g.blk_start + p.RB);
   g.ntiles = (g.blk_end - g.blk_start + kTile - 1) / kTile;
-  g.nchunks = (g.ntiles + g.nwarps - 1) / g.nwarps;
+  g.npass = (g.ntiles + g.ncw - 1) / g.ncw;
   g.ngroups = (p.L + tps - 1) / tps;
+  g.prows = g.ncw * kTile;
 }
 
-__device__ __forceinline__ int last_chunk_of_warp(const WarpGeom& g) {
-  return (g.ntiles - 1 - g.warp) / g.nwarps;  // largest c with c*nwarps + warp < ntiles
+// Shared-memory carve-up (bytes from the start of dynamic smem):
+//   [0, 8*plane*4)                      state block, channel-major
+//   then ring: stages * tps * slot floats   (slot = ncw*128 (+8 backward))
+//   then mbarriers: full[stages], empty[stages], vbar
+struct Smem {
+  float* state;
+  uint32_t ring_u32, full_u32, empty_u32, vbar_u32, state_u32;
+  const float* ring;
+  int slot;        // floats per tap window
+  int stage_f;     // floats per stage
+  const int* offs;         // [32] offset of the tap visited i-th (copied from the kernel parameters:
+  const long long* tapoff; // [32]  indexing parameter arrays dynamically compiles to select chains)
+};
+
+template <int kPlane>
+__device__ __forceinline__ void carve(Smem& sm, unsigned char* raw, const FusedParams& p, int tps, int pad) {
+  sm.state = reinterpret_cast<float*>(raw);
+  float* ring = sm.state + CT * kPlane;
+  sm.ring = ring;
+  sm.slot = p.ncw * kTile + pad;
+  sm.stage_f = tps * sm.slot;
+  sm.state_u32 = smem_u32(sm.state);
+  sm.ring_u32 = smem_u32(ring);
+  sm.full_u32 = sm.ring_u32 + (uint32_t)(p.stages * sm.stage_f) * 4u;
+  sm.empty_u32 = sm.full_u32 + (uint32_t)p.stages * 8u;
+  sm.vbar_u32 = sm.empty_u32 + (uint32_t)p.stages * 8u;
+  unsigned char* tab = reinterpret_cast<unsigned char*>(ring + p.stages * sm.stage_f) + (2 * p.stages + 2) * 8;
+  sm.tapoff = reinterpret_cast<const long long*>(tab);
+  sm.offs = reinterpret_cast<const int*>(tab + PSF_MAX_TAPS * 8);
 }
 
-template <bool kBackward>
-__device__ __forceinline__ void cursor_tile(WCursor& cur, const FusedParams& p, const WarpGeom& g) {
-  const int tile = cur.c * g.nwarps + g.warp;
-  cur.row0 = g.blk_start + tile * kTile;
-  cur.rw = min(kTile, g.blk_end - cur.row0);
-  cur.wptr = p.W + (long long)(cur.m - 1) * p.sWf + (long long)cur.b * p.sWb + (kBackward ? 0 : cur.row0);
+// ---------------------------------------------------------------------------------------------
+// W producer.  Warp 0 carries a cursor over every (sample, factor, pass, tap group) of this CTA, in
+// the exact order the stages are consumed; at each stage boundary its lane 0 tops the ring up with
+// whatever slots every warp has released (non-blocking test of the empty barrier), and only blocks
+// if the stage it is about to consume itself has not been issued yet.
+// ---------------------------------------------------------------------------------------------
+struct Producer {
+  int b, mm, pp, tg;   // next stage to issue
+  int slot;            // ring slot it goes to
+  uint32_t ph;         // empty-barrier parity to test (1 on a fresh barrier)
+  int ahead;           // stages issued and not yet consumed by warp 0
+  bool valid;
+};
+
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
 }
 
-template <bool kBackward>
-__device__ __forceinline__ void cursor_init(WCursor& cur, const FusedParams& p, const WarpGeom& g) {
-  cur.b = g.cid;
-  cur.tg = 0;
-  cur.valid = (g.warp < g.ntiles) && (cur.b < p.B) && (p.n_W > 0);
-  if (kBackward) {
-    cur.m = p.n_W;
-    cur.c = cur.valid ? last_chunk_of_warp(g) : 0;
-  } else {
-    cur.m = 1;
-    cur.c = 0;
-  }
-  if (cur.valid) cursor_tile<kBackward>(cur, p, g);
+__device__ __forceinline__ void producer_init(Producer& pr, const FusedParams& p, const Geom& g) {
+  pr.b = g.cid;
+  pr.mm = 0;
+  pr.pp = 0;
+  pr.tg = 0;
+  pr.slot = 0;
+  pr.ph = 1u;
+  pr.ahead = 0;
+  pr.valid = (pr.b < p.B) && (g.npass > 0);
 }
 
-template <bool kBackward>
-__device__ __forceinline__ void cursor_next(WCursor& cur, const FusedParams& p, const WarpGeom& g) {
-  if (++cur.tg < g.ngroups) return;
-  cur.tg = 0;
-  bool wrapped = false;
-  if (kBackward) {
-    if (--cur.c < 0) {
-      cur.c = last_chunk_of_warp(g);
-      if (--cur.m < 1) {
-        cur.m = p.n_W;
-        wrapped = true;
+// Issue the stage under the cursor (lane 0 of warp 0 only) and advance the cursor (all lanes).
+template <bool kBackward, int kTps>
+__device__ __forceinline__ void producer_issue(Producer& pr, const FusedParams& p, const Geom& g, const Smem& sm) {
+  if (g.lane == 0) {
+    const int m = kBackward ? p.n_W - pr.mm : pr.mm + 1;
+    const float* wfac = p.W + (long long)(m - 1) * p.sWf + (long long)pr.b * p.sWb;
+    const int row0 = g.blk_start + pr.pp * g.prows;
+    const int prow = min(g.prows, g.blk_end - row0);
+    const uint32_t bar = sm.full_u32 + pr.slot * 8;
+    const uint32_t dst = sm.ring_u32 + (uint32_t)(pr.slot * sm.stage_f) * 4u;
+    const int i0 = pr.tg * kTps;
+    if (!kBackward) {
+      const int kn = min(kTps, p.L - i0);
+      const uint32_t bytes = (uint32_t)prow * 4u;
+      mbar_expect_tx(bar, bytes * (uint32_t)kn);
+#pragma unroll
+      for (int t = 0; t < kTps; ++t)
+        if (t < kn) tma_load_1d(dst + (uint32_t)(t * sm.slot) * 4u, wfac + sm.tapoff[i0 + t] + row0, bytes, bar);
+    } else {
+      uint32_t total = 0;
+#pragma unroll
+      for (int t = 0; t < kTps; ++t)
+        if (i0 + t < p.L) total += (uint32_t)(prow + ((sm.offs[i0 + t] & 3) ? 4 : 0)) * 4u;
+      mbar_expect_tx(bar, total);
+#pragma unroll
+      for (int t = 0; t < kTps; ++t) {
+        if (i0 + t < p.L) {
+          const int o = sm.offs[i0 + t];
+          int s0 = row0 - o;
+          if (s0 < 0) s0 += p.n;
+          const int a0 = s0 & ~3;                    // 16 B aligned start of the source window
+          const int len = prow + ((o & 3) ? 4 : 0);  // floats
+          const int first = min(len, p.n - a0);      // part before the cyclic wrap
+          const float* wk = wfac + sm.tapoff[i0 + t];
+          const uint32_t d = dst + (uint32_t)(t * sm.slot) * 4u;
+          tma_load_1d(d, wk + a0, (uint32_t)first * 4u, bar);
+          if (first < len) tma_load_1d(d + (uint32_t)first * 4u, wk, (uint32_t)(len - first) * 4u, bar);
+        }
       }
     }
-  } else {
-    ++cur.c;
-    if (cur.c * g.nwarps + g.warp >= g.ntiles) {
-      cur.c = 0;
-      if (++cur.m > p.n_W) {
-        cur.m = 1;
-        wrapped = true;
+  }
+  ++pr.ahead;
+  if (++pr.slot == p.stages) {
+    pr.slot = 0;
+    pr.ph ^= 1u;
+  }
+  if (++pr.tg == g.ngroups) {
+    pr.tg = 0;
+    if (++pr.pp == g.npass) {
+      pr.pp = 0;
+      if (++pr.mm == p.n_W) {
+        pr.mm = 0;
+        pr.b += g.ncl;
+        pr.valid = pr.b < p.B;
       }
     }
   }
-  if (wrapped) {
-    cur.b += g.ncl;
-    cur.valid = cur.b < p.B;
-  }
-  if (cur.valid) cursor_tile<kBackward>(cur, p, g);
 }
 
-// Lane 0: arm the stage barrier and launch the bulk copies of one stage (<= kTps taps).
-template <bool kBackward, int kTps, int kSlot>
-__device__ __forceinline__ void issue_stage(const WCursor& cur, const FusedParams& p, uint32_t dst, uint32_t bar) {
-  const int i0 = cur.tg * kTps;
-  if (!kBackward) {
-    const uint32_t bytes = (uint32_t)cur.rw * 4u;
-    const int kn = min(kTps, p.L - i0);
-    mbar_expect_tx(bar, bytes * (uint32_t)kn);
-#pragma unroll
-    for (int t = 0; t < kTps; ++t)
-      if (t < kn) tma_load_1d(dst + t * kSlot * 4, cur.wptr + p.tapoff[i0 + t], bytes, bar);
-  } else {
-    uint32_t total = 0;
-#pragma unroll
-    for (int t = 0; t < kTps; ++t)
-      if (i0 + t < p.L) total += (uint32_t)(cur.rw + ((p.ooffs.o[i0 + t] & 3) ? 4 : 0)) * 4u;
-    mbar_expect_tx(bar, total);
-#pragma unroll
-    for (int t = 0; t < kTps; ++t) {
-      if (i0 + t < p.L) {
-        const int o = p.ooffs.o[i0 + t];
-        int s0 = cur.row0 - o;
-        if (s0 < 0) s0 += p.n;
-        const int a0 = s0 & ~3;                      // 16 B aligned start of the source window
-        const int len = cur.rw + ((o & 3) ? 4 : 0);  // floats
-        const int first = min(len, p.n - a0);        // part before the cyclic wrap
-        const float* wk = cur.wptr + p.tapoff[i0 + t];
-        tma_load_1d(dst + t * kSlot * 4, wk + a0, (uint32_t)first * 4u, bar);
-        if (first < len) tma_load_1d(dst + (t * kSlot + first) * 4, wk, (uint32_t)(len - first) * 4u, bar);
-      }
+// Top the ring up.  must_have: warp 0 is about to consume a stage, so at least one must be in flight.
+template <bool kBackward, int kTps>
+__device__ __forceinline__ void producer_pump(Producer& pr, const FusedParams& p, const Geom& g, const Smem& sm,
+                                              bool must_have) {
+  while (pr.valid && pr.ahead < p.stages) {
+    const uint32_t bar = sm.empty_u32 + pr.slot * 8;
+    if (!mbar_test(bar, pr.ph)) {
+      if (!(must_have && pr.ahead == 0)) break;
+      mbar_wait(bar, pr.ph);
     }
+    producer_issue<kBackward, kTps>(pr, p, g, sm);
   }
+}
+
+// Consumer warp 0 / lane 0: pull this CTA's block of a channel-major global state into shared memory.
+template <int kPlane>
+__device__ __forceinline__ void refresh_state(const Smem& sm, const Geom& g, const float* state_b, int n) {
+  const uint32_t bytes = (uint32_t)(g.blk_end - g.blk_start) * 4u;
+  if (bytes == 0) {  // empty block: complete the phase without a copy
+    mbar_arrive(sm.vbar_u32);
+    return;
+  }
+  mbar_expect_tx(sm.vbar_u32, bytes * CT);
+#pragma unroll
+  for (int ch = 0; ch < CT; ++ch)
+    tma_load_1d(sm.state_u32 + (uint32_t)(ch * kPlane) * 4u, state_b + (long long)ch * n + g.blk_start, bytes,
+                sm.vbar_u32);
+}
+
+__device__ __forceinline__ void init_barriers(const FusedParams& p, const Smem& sm) {
+  if (threadIdx.x == 0) {
+    int* so = const_cast<int*>(sm.offs);
+    long long* st = const_cast<long long*>(sm.tapoff);
+#pragma unroll
+    for (int i = 0; i < PSF_MAX_TAPS; ++i) {
+      so[i] = p.ooffs.o[i];
+      st[i] = p.tapoff[i];
+    }
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(sm.full_u32 + s * 8, 1);
+      mbar_init(sm.empty_u32 + s * 8, (uint32_t)p.ncw);
+    }
+    mbar_init(sm.vbar_u32, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------
 // Forward
 // ---------------------------------------------------------------------------------------------
 template <int kPlane>
-__global__ void __launch_bounds__(kMaxThreads, 1) psf_chain_fwd_kernel(const FusedParams p) {
+__global__ void __launch_bounds__(kMaxThreads, (kPlane <= 2048 ? 2 : 1)) psf_chain_fwd_kernel(const FusedParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int kTps = kTpsF, kSlot = kSlotF;
-  WarpGeom g;
+  constexpr int kTps = kTpsF;
+  Geom g;
   make_geom(g, p, kTps);
+  Smem sm;
+  carve<kPlane>(sm, smem_raw, p, kTps, 0);
+  init_barriers(p, sm);
 
-  float* Vs = reinterpret_cast<float*>(smem_raw);  // [CT][kPlane], rows [0, p.RB) of every plane in use
-  constexpr int RB = kPlane;                       // compile-time plane stride -> immediate LDS offsets
+  Producer pr;
+  producer_init(pr, p, g);
+  if (g.warp == 0 && !(p.dbg & 8)) producer_pump<false, kTps>(pr, p, g, sm, false);
+
   const int S = p.stages;
-  float* ring = Vs + CT * RB + (size_t)g.warp * S * kTps * kSlot;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Vs + CT * RB + (size_t)g.nwarps * S * kTps * kSlot) + g.warp * S;
-
-  const uint32_t ring_u32 = smem_u32(ring), bars_u32 = smem_u32(bars);
-  if (g.lane == 0) {
-    for (int s = 0; s < S; ++s) mbar_init(bars_u32 + s * 8, 1);
-    fence_barrier_init();
-  }
-  __syncwarp();
-
-  WCursor cur;
-  cursor_init<false>(cur, p, g);
-  for (int s = 0; s < S; ++s) {  // prime the ring
-    if (cur.valid) {
-      if (g.lane == 0) issue_stage<false, kTps, kSlot>(cur, p, ring_u32 + s * (kTps * kSlot * 4), bars_u32 + s * 8);
-      cursor_next<false>(cur, p, g);
-    }
-  }
-  int slot = 0;          // ring slot consumed next (same on all lanes)
-  uint32_t parity = 0;   // its mbarrier phase
-
+  const int nthr_c = g.ncw * 32;
+  const float* Vs = sm.state;
   const int n = p.n;
-  const int64_t plane = (int64_t)CT * n;  // floats per sample per state
+  const long long plane = (long long)CT * n;  // floats per sample per state
+  int slot = 0;
+  uint32_t parity = 0, vparity = 0;
+  const bool refresher = (threadIdx.x == 0);
 
   for (int b = g.cid; b < p.B; b += g.ncl) {
-    // ---- prologue: V0 block -> shared (channel-major) + state slot 0 --------------------
-    float* st0 = p.states + (int64_t)b * plane;  // slot 0 of this sample
-    for (int c = 0; c < g.nchunks; ++c) {
-      const int tile = c * g.nwarps + g.warp;
-      const int j = g.blk_start + tile * kTile + 4 * g.lane;
-      if (tile < g.ntiles && j < g.blk_end) {
+    // ---- prologue: V0 block -> state slot 0 (channel-major) ------------------------------
+    float* st0 = p.states + (long long)b * plane;
+    for (int pp = 0; pp < g.npass; ++pp) {
+      const int j = g.blk_start + (pp * g.ncw + g.warp) * kTile + 4 * g.lane;
+      if (j < g.blk_end) {
         float4 pl[CT];
-        load_rows_natural(p.Vin + ((int64_t)b * n + j) * CT, pl);
+        load_rows_natural(p.Vin + ((long long)b * n + j) * CT, pl);
 #pragma unroll
-        for (int ch = 0; ch < CT; ++ch) {
-          *reinterpret_cast<float4*>(Vs + ch * RB + (j - g.blk_start)) = pl[ch];
-          st_cg4(st0 + ch * n + j, pl[ch]);
-        }
+        for (int ch = 0; ch < CT; ++ch) st_cg4(st0 + ch * n + j, pl[ch]);
       }
     }
-    cluster_sync_all();
+    fence_proxy_async();
+    consumer_bar_sync(nthr_c);  // the block is written; nobody reads the shared copy any more
+    if (refresher) refresh_state<kPlane>(sm, g, st0, n);
+    cluster_arrive();
+    cluster_wait();
 
     for (int m = 1; m <= p.n_W; ++m) {
       // slot 0 always keeps V_0 (residual operand); without saved states slots 1/2 alternate
       const int slot_prev = (p.save_states || m == 1) ? (m - 1) : 1 + ((m - 1) & 1);
       const int slot_next = p.save_states ? m : 1 + (m & 1);
-      const float* prev = p.states + ((int64_t)slot_prev * p.B + b) * plane;
-      float* next = p.states + ((int64_t)slot_next * p.B + b) * plane;
+      const float* prev = p.states + ((long long)slot_prev * p.B + b) * plane;
+      float* next = p.states + ((long long)slot_next * p.B + b) * plane;
       const bool last = (m == p.n_W);
 
-      for (int c = 0; c < g.nchunks; ++c) {
-        const int tile = c * g.nwarps + g.warp;
-        const bool active = tile < g.ntiles;
-        const int row0 = g.blk_start + tile * kTile;
+      mbar_wait(sm.vbar_u32, vparity);  // V_{m-1} block has landed in shared memory
+      vparity ^= 1u;
+
+      for (int pp = 0; pp < g.npass; ++pp) {
+        const int row0 = g.blk_start + (pp * g.ncw + g.warp) * kTile;
         const int j = row0 + 4 * g.lane;
-        const bool mine = active && (j < g.blk_end);
+        const bool mine = j < g.blk_end;
         float4 acc[CT];
 #pragma unroll
         for (int ch = 0; ch < CT; ++ch) acc[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-        if (active) {
-          // one global-operand tap in flight: issued here, consumed after the next local taps
-          bool pend = false;
-          float4 pw = make_float4(1.f, 1.f, 1.f, 1.f);
-          float4 pv[CT];
-          if (mine && p.residual) {  // the residual V_0 rides the pending slot with weight 1
+        // one global-operand tap in flight: issued here, consumed after the next local taps
+        bool pend = false;
+        float4 pw = make_float4(1.f, 1.f, 1.f, 1.f);
+        float4 pv[CT];
+        if (mine && p.residual && !(p.dbg & 32)) {  // the residual V_0 rides the pending slot with weight 1
 #pragma unroll
-            for (int ch = 0; ch < CT; ++ch) pv[ch] = ld_cg4(st0 + ch * n + j);
-            pend = true;
+          for (int ch = 0; ch < CT; ++ch) pv[ch] = ld_cg4(st0 + ch * n + j);
+          pend = true;
+        }
+        const float* vown = Vs + (j - g.blk_start);
+        for (int tg = 0; tg < g.ngroups; ++tg) {
+          if (!(p.dbg & 8)) {
+            if (g.warp == 0 && pr.ahead == 0) producer_pump<false, kTps>(pr, p, g, sm, true);
+            mbar_wait(sm.full_u32 + slot * 8, parity);
           }
-          const float* vown = Vs + (j - g.blk_start);
-          for (int tg = 0; tg < g.ngroups; ++tg) {
-            const int s = slot;
-            mbar_wait(bars_u32 + s * 8, parity);
-            const float* wst = ring + s * kTps * kSlot + 4 * g.lane;
-            if (mine) {
-              if (tg == 0 && p.head) {
-                // taps with offsets 0,1,2,4 share the quads A = rows j..j+3 and Bq = rows j+4..j+7
-                const float4 w0 = lds4(wst), w1 = lds4(wst + kSlot), w2 = lds4(wst + 2 * kSlot),
-                             w3 = lds4(wst + 3 * kSlot);
-                const bool bq_local = (j + 8 <= g.blk_end);
-                const int jb = (j + 4 >= n) ? j + 4 - n : j + 4;
+          const float* wst = sm.ring + slot * sm.stage_f + g.warp * kTile + 4 * g.lane;
+          if (mine) {
+            if (tg == 0 && p.head) {
+              // taps with offsets 0,1,2,4 share the quads A = rows j..j+3 and Bq = rows j+4..j+7
+              const float4 w0 = lds4(wst), w1 = lds4(wst + sm.slot), w2 = lds4(wst + 2 * sm.slot),
+                           w3 = lds4(wst + 3 * sm.slot);
+              const bool bq_local = (j + 8 <= g.blk_end);
+              const int jb = (j + 4 >= n) ? j + 4 - n : j + 4;
 #pragma unroll
-                for (int ch = 0; ch < CT; ++ch) {
-                  const float4 A = lds4(vown + ch * RB);
-                  const float4 Bq = bq_local ? lds4(vown + ch * RB + 4) : ld_cg4(prev + ch * n + jb);
-                  // row r: w0[r]*V[j+r] + w1[r]*V[j+r+1] + w2[r]*V[j+r+2] + w3[r]*V[j+r+4]
-                  fma4(acc[ch], w0, A);                                   // tap 0
-                  fma4(acc[ch], w3, Bq);                                  // tap 4
-                  fma2(acc[ch].x, acc[ch].y, w2.x, w2.y, A.z, A.w);       // tap 2, rows 0-1
-                  fma2(acc[ch].z, acc[ch].w, w2.z, w2.w, Bq.x, Bq.y);     // tap 2, rows 2-3
-                  acc[ch].x = fmaf(w1.x, A.y, acc[ch].x);                 // tap 1
-                  acc[ch].y = fmaf(w1.y, A.z, acc[ch].y);
-                  acc[ch].z = fmaf(w1.z, A.w, acc[ch].z);
-                  acc[ch].w = fmaf(w1.w, Bq.x, acc[ch].w);
-                }
-              } else {
+              for (int ch = 0; ch < CT; ++ch) {
+                const float4 A = lds4(vown + ch * kPlane);
+                const float4 Bq = bq_local ? lds4(vown + ch * kPlane + 4) : ld_cg4(prev + ch * n + jb);
+                // row r: w0[r]*V[j+r] + w1[r]*V[j+r+1] + w2[r]*V[j+r+2] + w3[r]*V[j+r+4]
+                fma4(acc[ch], w0, A);                                // offset 0
+                fma4(acc[ch], w3, Bq);                               // offset 4
+                fma2(acc[ch].x, acc[ch].y, w2.x, w2.y, A.z, A.w);    // offset 2, rows 0-1
+                fma2(acc[ch].z, acc[ch].w, w2.z, w2.w, Bq.x, Bq.y);  // offset 2, rows 2-3
+                acc[ch].x = fmaf(w1.x, A.y, acc[ch].x);              // offset 1
+                acc[ch].y = fmaf(w1.y, A.z, acc[ch].y);
+                acc[ch].z = fmaf(w1.z, A.w, acc[ch].z);
+                acc[ch].w = fmaf(w1.w, Bq.x, acc[ch].w);
+              }
+            } else {
 #pragma unroll
-                for (int t = 0; t < kTps; ++t) {
-                  const int i = tg * kTps + t;
-                  if (i < p.L) {
-                    const float4 w4 = lds4(wst + t * kSlot);
-                    const int o = p.ooffs.o[i];
-                    const int src = j + o;
-                    if ((o & 3) == 0) {
-                      if (src + 4 <= g.blk_end) {
-                        const float* vp = vown + o;
+              for (int t = 0; t < kTps; ++t) {
+                const int i = tg * kTps + t;
+                if (i < p.L) {
+                  const float4 w4 = lds4(wst + t * sm.slot);
+                  const int o = sm.offs[i];
+                  const int src = j + o;
+                  if ((o & 3) == 0) {
+                    if (src + 4 <= g.blk_end || (p.dbg & 4)) {
+                      const float* vp = (p.dbg & 4) ? Vs + ((src - g.blk_start) & (kPlane - 4)) : vown + o;
+                      float4 v[CT];
 #pragma unroll
-                        for (int ch = 0; ch < CT; ++ch) fma4(acc[ch], w4, lds4(vp + ch * RB));
-                      } else {
-                        if (pend) {
+                      for (int ch = 0; ch < CT; ++ch) v[ch] = lds4(vp + ch * kPlane);
 #pragma unroll
-                          for (int ch = 0; ch < CT; ++ch) fma4(acc[ch], pw, pv[ch]);
-                        }
-                        const float* gp = prev + (src >= n ? src - n : src);
-                        pw = w4;
-#pragma unroll
-                        for (int ch = 0; ch < CT; ++ch) pv[ch] = ld_cg4(gp + ch * n);
-                        pend = true;
-                      }
+                      for (int ch = 0; ch < CT; ++ch) fma4(acc[ch], w4, v[ch]);
                     } else {
-                      // unaligned tap: the two aligned quads covering rows src..src+3, select in registers
-                      const int sh = o & 3;
-                      const int a = src - sh;
-                      const bool xl = (a + 4 <= g.blk_end), yl = (a + 8 <= g.blk_end);
-                      const int ax = a >= n ? a - n : a;
-                      const int ay = (a + 4 >= n) ? a + 4 - n : a + 4;
+                      if (pend) {
 #pragma unroll
-                      for (int ch = 0; ch < CT; ++ch) {
-                        const float4 X = xl ? lds4(vown + (o - sh) + ch * RB) : ld_cg4(prev + ch * n + ax);
-                        const float4 Y = yl ? lds4(vown + (o - sh) + 4 + ch * RB) : ld_cg4(prev + ch * n + ay);
-                        fma4(acc[ch], w4, select_quad(X, Y, sh));
+                        for (int ch = 0; ch < CT; ++ch) fma4(acc[ch], pw, pv[ch]);
                       }
+                      const float* gp = prev + (src >= n ? src - n : src);
+                      pw = w4;
+#pragma unroll
+                      for (int ch = 0; ch < CT; ++ch) pv[ch] = ld_cg4(gp + ch * n);
+                      pend = true;
+                    }
+                  } else {
+                    // unaligned tap: the two aligned quads covering rows src..src+3, select in registers
+                    const int sh = o & 3;
+                    const int a = src - sh;
+                    const bool xl = (a + 4 <= g.blk_end), yl = (a + 8 <= g.blk_end);
+                    const int ax = a >= n ? a - n : a;
+                    const int ay = (a + 4 >= n) ? a + 4 - n : a + 4;
+#pragma unroll
+                    for (int ch = 0; ch < CT; ++ch) {
+                      const float4 X = xl ? lds4_full(vown + (o - sh) + ch * kPlane) : ld_cg4(prev + ch * n + ax);
+                      const float4 Y = yl ? lds4_full(vown + (o - sh) + 4 + ch * kPlane) : ld_cg4(prev + ch * n + ay);
+                      fma4(acc[ch], w4, select_quad(X, Y, sh));
                     }
                   }
                 }
               }
             }
-            __syncwarp();
+          }
+          __syncwarp();
+          if (!(p.dbg & 8)) {
+            if (g.lane == 0) mbar_arrive(sm.empty_u32 + slot * 8);  // this warp is done with the stage
             if (++slot == S) {
               slot = 0;
               parity ^= 1u;
             }
-            if (cur.valid) {  // refill the slot just drained
-              if (g.lane == 0) issue_stage<false, kTps, kSlot>(cur, p, ring_u32 + s * (kTps * kSlot * 4), bars_u32 + s * 8);
-              cursor_next<false>(cur, p, g);
+            if (g.warp == 0) {
+              --pr.ahead;
+              producer_pump<false, kTps>(pr, p, g, sm, false);
             }
           }
+        }
+        if (mine) {
           if (pend) {
 #pragma unroll
             for (int ch = 0; ch < CT; ++ch) fma4(acc[ch], pw, pv[ch]);
           }
-        }
-        __syncthreads();  // every read of this chunk's rows (by this chunk and all lower ones) is done
-        if (mine) {
           if (!last) {
+            if (!(p.dbg & 1) || acc[0].x == 123.456f) {
 #pragma unroll
-            for (int ch = 0; ch < CT; ++ch) {
-              *reinterpret_cast<float4*>(Vs + ch * RB + (j - g.blk_start)) = acc[ch];
-              st_cg4(next + ch * n + j, acc[ch]);
+              for (int ch = 0; ch < CT; ++ch) st_cg4(next + ch * n + j, acc[ch]);
             }
           } else {
-            store_rows_natural(p.Vout + ((int64_t)b * n + j) * CT, acc);
+            store_rows_natural(p.Vout + ((long long)b * n + j) * CT, acc);
           }
         }
       }
-      cluster_sync_all();  // V_m visible cluster-wide (global) and CTA-wide (shared)
-    }
-    if (p.n_W == 0) {  // degenerate: out = V0
-      for (int c = 0; c < g.nchunks; ++c) {
-        const int tile = c * g.nwarps + g.warp;
-        const int j = g.blk_start + tile * kTile + 4 * g.lane;
-        if (tile < g.ntiles && j < g.blk_end) {
-          float4 pl[CT];
-#pragma unroll
-          for (int ch = 0; ch < CT; ++ch) pl[ch] = lds4(Vs + ch * RB + (j - g.blk_start));
-          store_rows_natural(p.Vout + ((int64_t)b * n + j) * CT, pl);
+      if (!last) {
+        fence_proxy_async();
+        consumer_bar_sync(nthr_c);  // all reads of the shared block and all writes of V_m are done
+        if (refresher) {
+          if (p.dbg & 16) mbar_arrive(sm.vbar_u32); else refresh_state<kPlane>(sm, g, next, n);
+        }
+        if (!(p.dbg & 2)) {
+          cluster_arrive();           // V_m visible cluster-wide
+          cluster_wait();
         }
       }
-      cluster_sync_all();
     }
   }
 }
@@ -498,172 +587,155 @@ __global__ void __launch_bounds__(kMaxThreads, 1) psf_chain_fwd_kernel(const Fus
 // Backward
 // ---------------------------------------------------------------------------------------------
 template <int kPlane>
-__global__ void __launch_bounds__(kMaxThreads, 1) psf_chain_bwd_kernel(const FusedParams p) {
+__global__ void __launch_bounds__(kMaxThreads, (kPlane <= 2048 ? 2 : 1)) psf_chain_bwd_kernel(const FusedParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int kTps = kTpsB, kSlot = kSlotB;
-  WarpGeom g;
+  constexpr int kTps = kTpsB;
+  Geom g;
   make_geom(g, p, kTps);
+  Smem sm;
+  carve<kPlane>(sm, smem_raw, p, kTps, kPadB);
+  init_barriers(p, sm);
 
-  float* Gs = reinterpret_cast<float*>(smem_raw);  // [CT][kPlane]
-  constexpr int RB = kPlane;
+  Producer pr;
+  producer_init(pr, p, g);
+  if (g.warp == 0) producer_pump<true, kTps>(pr, p, g, sm, false);
+
   const int S = p.stages;
-  float* ring = Gs + CT * RB + (size_t)g.warp * S * kTps * kSlot;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Gs + CT * RB + (size_t)g.nwarps * S * kTps * kSlot) + g.warp * S;
-
-  const uint32_t ring_u32 = smem_u32(ring), bars_u32 = smem_u32(bars);
-  if (g.lane == 0) {
-    for (int s = 0; s < S; ++s) mbar_init(bars_u32 + s * 8, 1);
-    fence_barrier_init();
-  }
-  __syncwarp();
-
-  WCursor cur;
-  cursor_init<true>(cur, p, g);
-  for (int s = 0; s < S; ++s) {
-    if (cur.valid) {
-      if (g.lane == 0) issue_stage<true, kTps, kSlot>(cur, p, ring_u32 + s * (kTps * kSlot * 4), bars_u32 + s * 8);
-      cursor_next<true>(cur, p, g);
-    }
-  }
-  int slot = 0;
-  uint32_t parity = 0;
-
+  const int nthr_c = g.ncw * 32;
+  const float* Gs = sm.state;
   const int n = p.n;
-  const int64_t plane = (int64_t)CT * n;
+  const long long plane = (long long)CT * n;
+  int slot = 0;
+  uint32_t parity = 0, vparity = 0;
+  const bool refresher = (threadIdx.x == 0);
 
   for (int b = g.cid; b < p.B; b += g.ncl) {
-    float* gx0 = p.gx + (int64_t)b * plane;          // exchange slot 0
-    float* gx1 = p.gx + ((int64_t)p.B + b) * plane;  // exchange slot 1
-    float* racc = p.racc + (int64_t)b * plane;
-    // ---- prologue: dOut block -> shared + exchange slot 0 ---------------------------------
-    for (int c = 0; c < g.nchunks; ++c) {
-      const int tile = c * g.nwarps + g.warp;
-      const int j = g.blk_start + tile * kTile + 4 * g.lane;
-      if (tile < g.ntiles && j < g.blk_end) {
+    float* gx0 = p.gx + (long long)b * plane;          // exchange slot 0
+    float* gx1 = p.gx + ((long long)p.B + b) * plane;  // exchange slot 1
+    float* racc = p.racc + (long long)b * plane;
+    // ---- prologue: dOut block -> exchange slot 0 (channel-major) ---------------------------
+    for (int pp = 0; pp < g.npass; ++pp) {
+      const int j = g.blk_start + (pp * g.ncw + g.warp) * kTile + 4 * g.lane;
+      if (j < g.blk_end) {
         float4 pl[CT];
-        load_rows_natural(p.Vin + ((int64_t)b * n + j) * CT, pl);
+        load_rows_natural(p.Vin + ((long long)b * n + j) * CT, pl);
 #pragma unroll
-        for (int ch = 0; ch < CT; ++ch) {
-          *reinterpret_cast<float4*>(Gs + ch * RB + (j - g.blk_start)) = pl[ch];
-          st_cg4(gx0 + ch * n + j, pl[ch]);
-        }
+        for (int ch = 0; ch < CT; ++ch) st_cg4(gx0 + ch * n + j, pl[ch]);
       }
     }
-    cluster_sync_all();
+    fence_proxy_async();
+    consumer_bar_sync(nthr_c);
+    if (refresher) refresh_state<kPlane>(sm, g, gx0, n);
+    cluster_arrive();
+    cluster_wait();
 
     for (int m = p.n_W; m >= 1; --m) {
       const int step = p.n_W - m;
       const float* gcur = (step & 1) ? gx1 : gx0;
       float* gnext = (step & 1) ? gx0 : gx1;
-      const float* vprev = p.states + ((int64_t)(m - 1) * p.B + b) * plane;  // V_{m-1}, channel-major
-      float* dwbase = p.dW + (int64_t)(m - 1) * p.sWf + (int64_t)b * p.sWb;
+      const float* vprev = p.states + ((long long)(m - 1) * p.B + b) * plane;  // V_{m-1}, channel-major
+      float* dwbase = p.dW + (long long)(m - 1) * p.sWf + (long long)b * p.sWb;
       const bool last = (m == 1);
+      const bool first = (m == p.n_W);
 
-      for (int c = g.nchunks - 1; c >= 0; --c) {
-        const int tile = c * g.nwarps + g.warp;
-        const bool active = tile < g.ntiles;
-        const int row0 = g.blk_start + tile * kTile;
+      mbar_wait(sm.vbar_u32, vparity);  // G_m block has landed in shared memory
+      vparity ^= 1u;
+
+      for (int pp = 0; pp < g.npass; ++pp) {
+        const int row0 = g.blk_start + (pp * g.ncw + g.warp) * kTile;
         const int j = row0 + 4 * g.lane;
-        const bool mine = active && (j < g.blk_end);
+        const bool mine = j < g.blk_end;
         float4 acc[CT];
+        float4 vown[CT];
 #pragma unroll
         for (int ch = 0; ch < CT; ++ch) acc[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 rsum[CT];  // residual: racc so far, loaded before the barrier, used after it
-
-        if (active) {
-          float4 vown[CT];
+        if (mine) {
+#pragma unroll
+          for (int ch = 0; ch < CT; ++ch) vown[ch] = ld_cg4(vprev + ch * n + j);
+        }
+        const float* gown = Gs + (j - g.blk_start);
+        for (int tg = 0; tg < g.ngroups; ++tg) {
+          if (g.warp == 0 && pr.ahead == 0) producer_pump<true, kTps>(pr, p, g, sm, true);
+          mbar_wait(sm.full_u32 + slot * 8, parity);
+          const float* wst = sm.ring + slot * sm.stage_f + g.warp * kTile + 4 * g.lane;
           if (mine) {
 #pragma unroll
-            for (int ch = 0; ch < CT; ++ch) vown[ch] = ld_cg4(vprev + ch * n + j);
-          }
-          const float* gown = Gs + (j - g.blk_start);
-          for (int tg = 0; tg < g.ngroups; ++tg) {
-            const int s = slot;
-            mbar_wait(bars_u32 + s * 8, parity);
-            const float* wst = ring + s * kTps * kSlot + 4 * g.lane;
-            if (mine) {
+            for (int t = 0; t < kTps; ++t) {
+              const int i = tg * kTps + t;
+              if (i < p.L) {
+                const int o = sm.offs[i];
+                const int src = j - o;  // first source row (may be negative: cyclic)
+                float* dwk = dwbase + sm.tapoff[i];
+                if ((o & 3) == 0) {
+                  const float4 w4 = lds4(wst + t * sm.slot);
+                  float4 gv[CT];
+                  int sw;
+                  if (src >= g.blk_start) {
+                    sw = src;
 #pragma unroll
-              for (int t = 0; t < kTps; ++t) {
-                const int i = tg * kTps + t;
-                if (i < p.L) {
-                  const int o = p.ooffs.o[i];
-                  const int src = j - o;  // first source row (may be negative: cyclic)
-                  float* dwk = dwbase + p.tapoff[i];
-                  if ((o & 3) == 0) {
-                    const float4 w4 = lds4(wst + t * kSlot);
-                    float4 gv[CT];
-                    int sw;
-                    if (src >= g.blk_start) {
-                      sw = src;
-#pragma unroll
-                      for (int ch = 0; ch < CT; ++ch) gv[ch] = lds4(gown - o + ch * RB);
-                    } else {
-                      sw = src < 0 ? src + n : src;
-                      const float* gp = gcur + sw;
-#pragma unroll
-                      for (int ch = 0; ch < CT; ++ch) gv[ch] = ld_cg4(gp + ch * n);
-                    }
-                    float4 dw = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                    for (int ch = 0; ch < CT; ++ch) {
-                      fma4(acc[ch], w4, gv[ch]);
-                      fma4(dw, gv[ch], vown[ch]);
-                    }
-                    st_cs4(dwk + sw, dw);
+                    for (int ch = 0; ch < CT; ++ch) gv[ch] = lds4(gown - o + ch * kPlane);
                   } else {
-                    // unaligned tap: aligned quads X = rows a..a+3, Y = rows a+4..a+7 cover src..src+3
-                    const int sh = (4 - (o & 3)) & 3;  // src mod 4 (j is a multiple of 4)
-                    const int a = src - sh;
-                    const bool xl = (a >= g.blk_start), yl = (a + 4 >= g.blk_start);
-                    const int ax = a < 0 ? a + n : a;
-                    const int ay = (a + 4 < 0) ? a + 4 + n : a + 4;
-                    const float4 w4 = select_quad(lds4(wst + t * kSlot), lds4(wst + t * kSlot + 4), sh);
-                    float4 dw = make_float4(0.f, 0.f, 0.f, 0.f);
+                    sw = src < 0 ? src + n : src;
+                    const float* gp = gcur + sw;
 #pragma unroll
-                    for (int ch = 0; ch < CT; ++ch) {
-                      const float4 X = xl ? lds4(gown - o - sh + ch * RB) : ld_cg4(gcur + ch * n + ax);
-                      const float4 Y = yl ? lds4(gown - o - sh + 4 + ch * RB) : ld_cg4(gcur + ch * n + ay);
-                      const float4 gq = select_quad(X, Y, sh);
-                      fma4(acc[ch], w4, gq);
-                      fma4(dw, gq, vown[ch]);
-                    }
-                    // rows src..src+3 (cyclic) of dW_k: not 16 B aligned -> four scalar stores
-                    int r0 = src < 0 ? src + n : src;
-                    __stcs(dwk + r0, dw.x);
-                    r0 = (r0 + 1 == n) ? 0 : r0 + 1;
-                    __stcs(dwk + r0, dw.y);
-                    r0 = (r0 + 1 == n) ? 0 : r0 + 1;
-                    __stcs(dwk + r0, dw.z);
-                    r0 = (r0 + 1 == n) ? 0 : r0 + 1;
-                    __stcs(dwk + r0, dw.w);
+                    for (int ch = 0; ch < CT; ++ch) gv[ch] = ld_cg4(gp + ch * n);
                   }
+                  float4 dw = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                  for (int ch = 0; ch < CT; ++ch) {
+                    fma4(acc[ch], w4, gv[ch]);
+                    fma4(dw, gv[ch], vown[ch]);
+                  }
+                  st_cs4(dwk + sw, dw);
+                } else {
+                  // unaligned tap: aligned quads X = rows a..a+3, Y = rows a+4..a+7 cover src..src+3.
+                  // The staged W window starts at the aligned-down row of (prow0 - o), i.e. `sh` floats early.
+                  const int sh = (4 - (o & 3)) & 3;  // src mod 4 (j and prow0 are multiples of 4)
+                  const int a = src - sh;
+                  const bool xl = (a >= g.blk_start), yl = (a + 4 >= g.blk_start);
+                  const int ax = a < 0 ? a + n : a;
+                  const int ay = (a + 4 < 0) ? a + 4 + n : a + 4;
+                  const float4 w4 = select_quad(lds4_full(wst + t * sm.slot), lds4_full(wst + t * sm.slot + 4), sh);
+                  float4 dw = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                  for (int ch = 0; ch < CT; ++ch) {
+                    const float4 X = xl ? lds4_full(gown - o - sh + ch * kPlane) : ld_cg4(gcur + ch * n + ax);
+                    const float4 Y = yl ? lds4_full(gown - o - sh + 4 + ch * kPlane) : ld_cg4(gcur + ch * n + ay);
+                    const float4 gq = select_quad(X, Y, sh);
+                    fma4(acc[ch], w4, gq);
+                    fma4(dw, gq, vown[ch]);
+                  }
+                  // rows src..src+3 (cyclic) of dW_k: not 16 B aligned -> four scalar stores
+                  int r0 = src < 0 ? src + n : src;
+                  __stcs(dwk + r0, dw.x);
+                  r0 = (r0 + 1 == n) ? 0 : r0 + 1;
+                  __stcs(dwk + r0, dw.y);
+                  r0 = (r0 + 1 == n) ? 0 : r0 + 1;
+                  __stcs(dwk + r0, dw.z);
+                  r0 = (r0 + 1 == n) ? 0 : r0 + 1;
+                  __stcs(dwk + r0, dw.w);
                 }
               }
             }
-            __syncwarp();
-            if (++slot == S) {
-              slot = 0;
-              parity ^= 1u;
-            }
-            if (cur.valid) {
-              if (g.lane == 0) issue_stage<true, kTps, kSlot>(cur, p, ring_u32 + s * (kTps * kSlot * 4), bars_u32 + s * 8);
-              cursor_next<true>(cur, p, g);
-            }
           }
-          // residual: fetch the running sum now, its latency hides behind the barrier
-          if (mine && p.residual && m != p.n_W) {
-#pragma unroll
-            for (int ch = 0; ch < CT; ++ch) rsum[ch] = ld_cg4(racc + ch * n + j);
+          __syncwarp();
+          if (g.lane == 0) mbar_arrive(sm.empty_u32 + slot * 8);
+          if (++slot == S) {
+            slot = 0;
+            parity ^= 1u;
+          }
+          if (g.warp == 0) {
+            --pr.ahead;
+            producer_pump<true, kTps>(pr, p, g, sm, false);
           }
         }
-        __syncthreads();
         if (mine) {
           // residual: dV0 also receives G_m of every factor (V_m = W_m V_{m-1} + V_0)
           if (p.residual) {
 #pragma unroll
             for (int ch = 0; ch < CT; ++ch) {
-              float4 own = lds4(Gs + ch * RB + (j - g.blk_start));
-              if (m != p.n_W) add4(own, rsum[ch]);
+              float4 own = lds4(gown + ch * kPlane);
+              if (!first) add4(own, ld_cg4(racc + ch * n + j));
               if (!last) {
                 st_cg4(racc + ch * n + j, own);
               } else {
@@ -673,29 +745,19 @@ __global__ void __launch_bounds__(kMaxThreads, 1) psf_chain_bwd_kernel(const Fus
           }
           if (!last) {
 #pragma unroll
-            for (int ch = 0; ch < CT; ++ch) {
-              *reinterpret_cast<float4*>(Gs + ch * RB + (j - g.blk_start)) = acc[ch];
-              st_cg4(gnext + ch * n + j, acc[ch]);
-            }
+            for (int ch = 0; ch < CT; ++ch) st_cg4(gnext + ch * n + j, acc[ch]);
           } else {
-            store_rows_natural(p.Vout + ((int64_t)b * n + j) * CT, acc);
+            store_rows_natural(p.Vout + ((long long)b * n + j) * CT, acc);
           }
         }
       }
-      cluster_sync_all();
-    }
-    if (p.n_W == 0) {
-      for (int c = 0; c < g.nchunks; ++c) {
-        const int tile = c * g.nwarps + g.warp;
-        const int j = g.blk_start + tile * kTile + 4 * g.lane;
-        if (tile < g.ntiles && j < g.blk_end) {
-          float4 pl[CT];
-#pragma unroll
-          for (int ch = 0; ch < CT; ++ch) pl[ch] = lds4(Gs + ch * RB + (j - g.blk_start));
-          store_rows_natural(p.Vout + ((int64_t)b * n + j) * CT, pl);
-        }
+      if (!last) {
+        fence_proxy_async();
+        consumer_bar_sync(nthr_c);
+        if (refresher) refresh_state<kPlane>(sm, g, gnext, n);
+        cluster_arrive();
+        cluster_wait();
       }
-      cluster_sync_all();
     }
   }
 }
@@ -705,10 +767,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) psf_chain_bwd_kernel(const Fus
 // ---------------------------------------------------------------------------------------------
 int plane_for(int RB) { return RB <= 512 ? 512 : (RB <= 2048 ? 2048 : 4096); }
 
-int smem_bytes_for(int RB, int threads, int stages, bool backward) {
-  const int nwarps = threads / 32;
-  const int ring = backward ? stages * kTpsB * kSlotB : stages * kTpsF * kSlotF;
-  return CT * plane_for(RB) * 4 + nwarps * ring * 4 + nwarps * stages * 8;
+int smem_bytes_for(int RB, int ncw, int stages, bool backward) {
+  const int slot = ncw * kTile + (backward ? kPadB : 0);
+  const int ring = stages * (backward ? kTpsB : kTpsF) * slot;
+  return CT * plane_for(RB) * 4 + ring * 4 + (2 * stages + 2) * 8 + PSF_MAX_TAPS * 12;
 }
 
 const void* fwd_kernel_for(int RB) {
@@ -736,16 +798,15 @@ int env_int(const char* name, int dflt) {
 bool g_attr_done = false;
 
 struct OccCache {
-  int P, threads, smem, backward, clusters;
+  int P, threads, smem, clusters;
   const void* kernel;
 };
-OccCache g_occ[16];
+OccCache g_occ[32];
 int g_occ_n = 0;
 
-int resident_clusters(const void* kernel, int P, int threads, int smem, int backward, int sms) {
+int resident_clusters(const void* kernel, int P, int threads, int smem, int sms) {
   for (int i = 0; i < g_occ_n; ++i)
-    if (g_occ[i].P == P && g_occ[i].threads == threads && g_occ[i].smem == smem && g_occ[i].backward == backward &&
-        g_occ[i].kernel == kernel)
+    if (g_occ[i].P == P && g_occ[i].threads == threads && g_occ[i].smem == smem && g_occ[i].kernel == kernel)
       return g_occ[i].clusters;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(P * sms * 2), 1, 1);
@@ -763,16 +824,16 @@ int resident_clusters(const void* kernel, int P, int threads, int smem, int back
     cudaGetLastError();
     return 0;
   }
-  if (g_occ_n < 16) g_occ[g_occ_n++] = {P, threads, smem, backward, nclusters, kernel};
+  if (g_occ_n < 32) g_occ[g_occ_n++] = {P, threads, smem, nclusters, kernel};
   return nclusters;
 }
 
 // Tap visiting order.  Forward: the {0,1,2,4} head first (if present), then big offsets interleaved
 // 1:3 with small ones so every (possibly remote) big tap is followed by local work.  Backward: natural.
-void make_order(const PsfChainArgs& a, bool backward, PsfOffsets* order, int* head) {
+void make_order(const PsfChainArgs& a, bool backward, int* order, int* head) {
   const int L = a.L;
   *head = 0;
-  for (int i = 0; i < PSF_MAX_TAPS; ++i) order->o[i] = i < L ? i : 0;
+  for (int i = 0; i < PSF_MAX_TAPS; ++i) order[i] = i < L ? i : 0;
   if (backward) return;
   bool used[PSF_MAX_TAPS] = {false};
   int pos = 0;
@@ -786,7 +847,7 @@ void make_order(const PsfChainArgs& a, bool backward, PsfOffsets* order, int* he
       }
   if (hk[0] >= 0 && hk[1] >= 0 && hk[2] >= 0 && hk[3] >= 0 && a.n >= 8) {
     *head = 1;
-    for (int w = 0; w < 4; ++w) order->o[pos++] = hk[w];
+    for (int w = 0; w < 4; ++w) order[pos++] = hk[w];
   } else {
     for (int k = 0; k < L; ++k) used[k] = false;
   }
@@ -806,10 +867,10 @@ void make_order(const PsfChainArgs& a, bool backward, PsfOffsets* order, int* he
   int lo = 0, hi = nr - 1, bigs = 0;
   while (lo <= hi) {
     if (bigs < nb) {
-      order->o[pos++] = rest[hi--];
+      order[pos++] = rest[hi--];
       ++bigs;
     }
-    for (int q = 0; q < 3 && lo <= hi; ++q) order->o[pos++] = rest[lo++];
+    for (int q = 0; q < 3 && lo <= hi; ++q) order[pos++] = rest[lo++];
   }
 }
 
@@ -834,7 +895,6 @@ int launch(const void* kernel, const FusedParams& fp, int P, int threads, int sm
 void fill_common(FusedParams& fp, const PsfChainArgs& a, const PsfFusedPlan& plan, bool backward) {
   fp.sWf = a.ws.factor;
   fp.sWb = a.ws.sample;
-  fp.sWt = a.ws.tap;
   fp.B = (int)a.B;
   fp.n = (int)a.n;
   fp.n_W = a.n_W;
@@ -843,54 +903,55 @@ void fill_common(FusedParams& fp, const PsfChainArgs& a, const PsfFusedPlan& pla
   fp.P = plan.cluster;
   fp.RB = plan.rows_per_cta;
   fp.stages = plan.stages;
-  fp.offs = a.offs;
-  make_order(a, backward, &fp.order, &fp.head);
+  fp.ncw = plan.threads / 32;
+  fp.dbg = env_int("PSF_FUSED_DEBUG", 0);
+  int order[PSF_MAX_TAPS];
+  make_order(a, backward, order, &fp.head);
   for (int i = 0; i < PSF_MAX_TAPS; ++i) {
-    fp.ooffs.o[i] = a.offs.o[fp.order.o[i]];
-    fp.tapoff[i] = (long long)fp.order.o[i] * a.ws.tap;
+    fp.ooffs.o[i] = a.offs.o[order[i]];
+    fp.tapoff[i] = (long long)order[i] * a.ws.tap;
   }
 }
 
 }  // namespace
 
 int psf_fused_plan(const PsfChainArgs& a, PsfFusedPlan* plan) {
-  if (a.C != CT || a.n < 4 || (a.n & 3) || a.L < 1 || a.L > PSF_MAX_TAPS || a.n_W < 0 || a.B < 1 ||
+  if (a.C != CT || a.n < 4 || (a.n & 3) || a.L < 1 || a.L > PSF_MAX_TAPS || a.n_W < 1 || a.B < 1 ||
       a.B > (1 << 20))
     return PSF_ERR_UNSUPPORTED;
   if (a.ws.row != 1 || (a.ws.factor & 3) || (a.ws.sample & 3) || (a.ws.tap & 3)) return PSF_ERR_UNSUPPORTED;
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) != cudaSuccess) return PSF_ERR_UNSUPPORTED;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  // block rows: 2048 (64 KB, two CTAs per SM) unless that needs more than 8 CTAs per sample
+  // block rows: 2048 (64 KB state, two CTAs per SM) unless that needs more than 8 CTAs per sample
   int max_rows = env_int("PSF_FUSED_MAX_ROWS", 2048);
-  int max_threads = env_int("PSF_FUSED_MAX_THREADS", 256);
-  if (max_threads > kMaxThreads) max_threads = kMaxThreads;
-  max_threads &= ~31;
-  if (max_threads < 32) max_threads = 32;
+  if (max_rows > 4096) max_rows = 4096;
   int P = 1;
   while ((a.n + P - 1) / P > max_rows && P < 8) P *= 2;
   if ((a.n + P - 1) / P > max_rows) {
     max_rows = 4096;
-    max_threads = kMaxThreads;
     if ((a.n + P - 1) / P > max_rows) return PSF_ERR_UNSUPPORTED;
   }
   // spread small batches over more SMs while a CTA keeps at least 4 warp tiles
-  while (P < 8 && a.B * P * 2 <= 2 * sms && (a.n + 2 * P - 1) / (2 * P) >= 4 * kTile) P *= 2;
+  while (P < 8 && a.B * P <= sms && (a.n + 2 * P - 1) / (2 * P) >= 4 * kTile) P *= 2;
   const int per = (int)((a.n + P - 1) / P);
   const int RB = (per + 3) & ~3;
-  int threads = ((RB + kTile - 1) / kTile) * 32;
-  if (threads > max_threads) threads = max_threads;
-  plan->cluster = P;
-  plan->rows_per_cta = RB;
-  plan->threads = threads;
+  int ncw = (RB + kTile - 1) / kTile;
+  const int max_cw = env_int("PSF_FUSED_CONSUMER_WARPS", kMaxCW);
+  if (ncw > max_cw) ncw = max_cw;
+  if (ncw > kMaxCW) ncw = kMaxCW;
+  const int threads = ncw * 32;
   int stages = env_int("PSF_FUSED_STAGES", 3);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
-  while (stages > 2 && smem_bytes_for(RB, threads, stages, true) > 227 * 1024) --stages;
-  if (smem_bytes_for(RB, threads, stages, true) > 227 * 1024) return PSF_ERR_UNSUPPORTED;
+  while (stages > 2 && smem_bytes_for(RB, ncw, stages, true) > 227 * 1024) --stages;
+  if (smem_bytes_for(RB, ncw, stages, true) > 227 * 1024) return PSF_ERR_UNSUPPORTED;
+  plan->cluster = P;
+  plan->rows_per_cta = RB;
+  plan->threads = threads;
   plan->stages = stages;
-  plan->smem_bytes = smem_bytes_for(RB, threads, stages, false);
-  plan->smem_bytes_bwd = smem_bytes_for(RB, threads, stages, true);
+  plan->smem_bytes = smem_bytes_for(RB, ncw, stages, false);
+  plan->smem_bytes_bwd = smem_bytes_for(RB, ncw, stages, true);
 
   if (!g_attr_done) {
     const int planes[3] = {512, 2048, 4096};
@@ -902,8 +963,8 @@ int psf_fused_plan(const PsfChainArgs& a, PsfFusedPlan* plan) {
         return PSF_ERR_UNSUPPORTED;
     g_attr_done = true;
   }
-  plan->resident = resident_clusters(fwd_kernel_for(RB), P, threads, plan->smem_bytes, 0, sms);
-  plan->resident_bwd = resident_clusters(bwd_kernel_for(RB), P, threads, plan->smem_bytes_bwd, 1, sms);
+  plan->resident = resident_clusters(fwd_kernel_for(RB), P, threads, plan->smem_bytes, sms);
+  plan->resident_bwd = resident_clusters(bwd_kernel_for(RB), P, threads, plan->smem_bytes_bwd, sms);
   if (plan->resident < 1 || plan->resident_bwd < 1) return PSF_ERR_UNSUPPORTED;
   return PSF_OK;
 }
@@ -935,14 +996,14 @@ int psf_fused_chain_bwd(const PsfChainArgs& a, const float* W, const float* dOut
   PsfFusedPlan plan;
   int rc = psf_fused_plan(a, &plan);
   if (rc) return rc;
-  const int64_t S = a.B * a.n * a.C;
+  const long long S = a.B * a.n * a.C;
   FusedParams fp = {};
   fp.W = W;
   fp.dW = dW;
   fp.Vin = dOut;
   fp.Vout = dV0;
   fp.states = ws;
-  fp.gx = ws + (int64_t)a.n_W * S;
+  fp.gx = ws + (long long)a.n_W * S;
   fp.racc = fp.gx + 2 * S;
   fp.save_states = 1;
   fill_common(fp, a, plan, true);
