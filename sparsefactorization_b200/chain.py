@@ -20,6 +20,47 @@ _DTYPES = {torch.float32: _capi.PSF_F32, torch.float64: _capi.PSF_F64}
 last_path_used: Optional[str] = None   # "fused" / "generic": which implementation the last forward took
 
 
+class _Stats:
+    """Launch counter and optional CUDA-event timing of the chain kernels (used by bench.py)."""
+
+    def __init__(self):
+        self.launches = 0          # calls into psf_chain_fwd / psf_chain_bwd that launched kernels
+        self.timing = False
+        self.events = {"fwd": [], "bwd": []}
+
+    def reset(self, timing: bool = False):
+        self.launches = 0
+        self.timing = timing
+        self.events = {"fwd": [], "bwd": []}
+
+    def mean_ms(self, kind: str) -> float:
+        """Mean device time of the recorded launches (call after torch.cuda.synchronize())."""
+        ev = self.events[kind]
+        return sum(a.elapsed_time(b) for a, b in ev) / len(ev) if ev else float("nan")
+
+
+stats = _Stats()
+
+
+class _Timed:
+    def __init__(self, kind):
+        self.kind = kind
+
+    def __enter__(self):
+        stats.launches += 1
+        if stats.timing:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()          # current stream == the stream the kernel is launched on
+        return self
+
+    def __exit__(self, *exc):
+        if stats.timing:
+            self.b.record()
+            stats.events[self.kind].append((self.a, self.b))
+        return False
+
+
 def _require_cuda(*tensors: torch.Tensor) -> None:
     for t in tensors:
         if not t.is_cuda:
@@ -89,8 +130,9 @@ class _ChordChainFn(torch.autograd.Function):
             ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=W.device)
             used = C.c_int(0)
             stream = torch.cuda.current_stream().cuda_stream
-            rc = lib.psf_chain_fwd(C.byref(d), W.data_ptr(), V0.data_ptr(), out.data_ptr(), ws.data_ptr(),
-                                   ws.numel(), 1 if need_grad else 0, C.byref(used), stream)
+            with _Timed("fwd"):
+                rc = lib.psf_chain_fwd(C.byref(d), W.data_ptr(), V0.data_ptr(), out.data_ptr(), ws.data_ptr(),
+                                       ws.numel(), 1 if need_grad else 0, C.byref(used), stream)
             _capi.check(rc, "psf_chain_fwd")
         last_path_used = _PATH_NAMES.get(used.value, str(used.value))
         if need_grad:
@@ -117,8 +159,9 @@ class _ChordChainFn(torch.autograd.Function):
             d = _desc(W, V_like, ctx.residual, offs_arr, ctx.path_used)   # same path as the forward: state layout
             used = C.c_int(0)
             stream = torch.cuda.current_stream().cuda_stream
-            rc = lib.psf_chain_bwd(C.byref(d), W.data_ptr(), dOut.data_ptr(), dW.data_ptr(), dV0.data_ptr(),
-                                   ctx.ws.data_ptr(), ctx.ws.numel(), C.byref(used), stream)
+            with _Timed("bwd"):
+                rc = lib.psf_chain_bwd(C.byref(d), W.data_ptr(), dOut.data_ptr(), dW.data_ptr(), dV0.data_ptr(),
+                                       ctx.ws.data_ptr(), ctx.ws.numel(), C.byref(used), stream)
             _capi.check(rc, "psf_chain_bwd")
         return dW, dV0, None, None, None
 

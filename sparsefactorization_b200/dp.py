@@ -1,0 +1,177 @@
+"""Data-parallel training of PSFNet: one process per GPU, batch sharded by rank, one flat-bucket
+gradient all-reduce per step (NCCL over NVLink on the GPU box, gloo in the CPU tests).
+
+The reference has no distributed code at all; this is the DP loop the north star
+asks for around the same ``TrainModel`` semantics (SyntheticExperiments/psf_utils.py:48-137).
+Design notes:
+  * every sample's chain is independent, so ranks exchange nothing on the data path; the only
+    collective is ``all_reduce(SUM)`` of the flattened parameter gradients followed by ``/ world``
+    (local-mean losses over equal shards average to the global-mean gradient);
+  * parameters that receive no gradient (``pos_embedding`` without positional embedding,
+    ``embedding`` for Adding) enter the bucket as zeros on every rank, so no
+    ``find_unused_parameters`` machinery is needed;
+  * ranks start from identical weights (broadcast from rank 0).
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def is_dist() -> bool:
+    return dist.is_available() and dist.is_initialized()
+
+
+def world_size() -> int:
+    return dist.get_world_size() if is_dist() else 1
+
+
+def rank() -> int:
+    return dist.get_rank() if is_dist() else 0
+
+
+def shard_range(n_items: int, rank_: Optional[int] = None, world: Optional[int] = None):
+    """Contiguous, equal shard of ``range(n_items)`` for a rank (the tail that does not divide is dropped)."""
+    rank_ = rank() if rank_ is None else rank_
+    world = world_size() if world is None else world
+    per = n_items // world
+    return rank_ * per, (rank_ + 1) * per
+
+
+class GradBucket:
+    """Flat fp32 bucket over the trainable parameters of a module."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        dev, dtype = self.params[0].device, self.params[0].dtype
+        self.sizes = [p.numel() for p in self.params]
+        self.flat = torch.zeros(sum(self.sizes), dtype=dtype, device=dev)
+        self.views = list(self.flat.split(self.sizes))
+
+    def pack(self) -> torch.Tensor:
+        for p, v in zip(self.params, self.views):
+            if p.grad is None:
+                v.zero_()
+            else:
+                v.copy_(p.grad.reshape(-1))
+        return self.flat
+
+    def unpack(self) -> None:
+        for p, v in zip(self.params, self.views):
+            g = v.view_as(p)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+
+
+class DataParallel:
+    """Minimal DP wrapper: ``broadcast_parameters()`` once, ``allreduce_gradients()`` after backward."""
+
+    def __init__(self, net: torch.nn.Module, process_group=None):
+        self.net = net
+        self.group = process_group
+        self.bucket = GradBucket(net.parameters())
+
+    def broadcast_parameters(self, src: int = 0) -> None:
+        if world_size() == 1:
+            return
+        with torch.no_grad():
+            for t in list(self.net.parameters()) + list(self.net.buffers()):
+                dist.broadcast(t.data, src=src, group=self.group)
+
+    def allreduce_gradients(self) -> None:
+        w = world_size()
+        if w == 1:
+            return
+        flat = self.bucket.pack()
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        flat.div_(w)
+        self.bucket.unpack()
+
+
+def train_step(net, dp: Optional[DataParallel], optimizer, loss_fn, X, Y, clip_grad_norm: Optional[float] = None):
+    """zero_grad -> forward -> loss -> backward -> (all-reduce) -> step.  Returns the detached local loss."""
+    optimizer.zero_grad(set_to_none=True)
+    pred = net(X)
+    out = loss_fn(pred.squeeze(), Y)
+    out.backward()
+    if dp is not None:
+        dp.allreduce_gradients()
+    if clip_grad_norm is not None:
+        torch.nn.utils.clip_grad_norm_(net.parameters(), max_norm=clip_grad_norm)
+    optimizer.step()
+    return out.detach()
+
+
+@torch.no_grad()
+def evaluate(net, X, Y, loss_fn, problem: str, batch_size: int):
+    """Loss / accuracy over this rank's shard, all-reduced to global values (percent accuracy)."""
+    dev = X.device
+    stats = torch.zeros(3, dtype=torch.float64, device=dev)   # loss_sum, correct, total
+    for i in range(0, X.shape[0] - batch_size + 1, batch_size):
+        xb, yb = X[i:i + batch_size], Y[i:i + batch_size]
+        pred = net(xb)
+        stats[0] += loss_fn(pred.squeeze(), yb).double() * yb.shape[0]
+        if problem == 'adding':
+            stats[1] += (torch.abs(pred.squeeze() - yb) < 0.04).sum()
+        else:
+            stats[1] += pred.max(1)[1].eq(yb).sum()
+        stats[2] += yb.shape[0]
+    if is_dist():
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    total = max(float(stats[2]), 1.0)
+    return float(stats[0]) / total, 100.0 * float(stats[1]) / total
+
+
+def TrainModelDP(net, train_data, val_data, test_data, n_epochs, test_freq, optimizer, loss, problem,
+                 saving_criteria, batch_size, shuffle_seed=0, verbose=True):
+    """Data-parallel counterpart of ``TrainModel``.
+
+    ``*_data`` are ``(X, Y)`` tensor pairs holding the FULL dataset on every rank (already on the
+    training device); each rank trains on its contiguous shard with per-GPU batch ``batch_size``.
+    Rank 0 prints the reference's per-epoch lines and saves the state dict under the same rule.
+    """
+    dp = DataParallel(net)
+    dp.broadcast_parameters()
+    Xtr, Ytr = train_data
+    lo, hi = shard_range(Xtr.shape[0])
+    Xs, Ys = Xtr[lo:hi], Ytr[lo:hi]
+    history = []
+    for epoch in range(n_epochs):
+        gen = torch.Generator(device=Xs.device).manual_seed(shuffle_seed + epoch * 7919 + rank())
+        perm = torch.randperm(Xs.shape[0], generator=gen, device=Xs.device)
+        running, steps = None, 0
+        for i in range(0, Xs.shape[0] - batch_size + 1, batch_size):
+            idx = perm[i:i + batch_size]
+            out = train_step(net, dp, optimizer, loss, Xs[idx], Ys[idx])
+            running = out if running is None else running + out
+            steps += 1
+        mean_loss = torch.zeros((), device=Xs.device) if running is None else running / max(steps, 1)
+        if is_dist():
+            dist.all_reduce(mean_loss, op=dist.ReduceOp.SUM)
+            mean_loss /= world_size()
+        rec = {"epoch": epoch, "train_loss": float(mean_loss)}
+        if epoch % test_freq == 0:
+            net.eval()
+            vs = shard_range(val_data[0].shape[0])
+            ts = shard_range(test_data[0].shape[0])
+            vl, va = evaluate(net, val_data[0][vs[0]:vs[1]], val_data[1][vs[0]:vs[1]], loss, problem, batch_size)
+            tl, ta = evaluate(net, test_data[0][ts[0]:ts[1]], test_data[1][ts[0]:ts[1]], loss, problem, batch_size)
+            net.train()
+            rec.update(val_loss=vl, val_acc=va, test_loss=tl, test_acc=ta)
+            if rank() == 0 and verbose:
+                print("Epoch {} - Training loss:  {}".format(epoch, rec["train_loss"]))
+                print("Val  loss: {}".format(vl))
+                print("Test loss: {}".format(tl))
+                print("Val  accuracy: {}".format(va))
+                print("Test accuracy: {}".format(ta))
+                print('_' * 40)
+            if rank() == 0 and ta > saving_criteria:
+                torch.save(net.state_dict(), '{}_epoch{}_acc{}.pt'.format(problem, epoch, ta))
+        history.append(rec)
+    return history
