@@ -95,6 +95,58 @@ def _same_structure(fs: Sequence[MLPBlock]) -> bool:
         getattr(l, "approximate", "none") == "none" for l in fs[0].network if isinstance(l, nn.GELU))
 
 
+class _TapMajorLastLinear(torch.autograd.Function):
+    """Last generator layer for all n_W factors, output tap-major.
+
+    h2d  ``[B*n, n_W*H]``  hidden activations of every generator side by side (one GEMM upstream)
+    w    ``[n_W, L, H]``, b ``[n_W, L]``
+    out  ``[n_W, L, B*n]`` = w[m] @ h_m^T + b[m]   (row index innermost: the chain's streaming order)
+
+    The backward pass is written out because autograd's version is pathological here: the weight
+    gradient is a GEMM with a 15 x 32 output and K = B*n (millions), for which cuBLAS falls back to a
+    gemv-style kernel (88 ms per step at B = 132).  It is evaluated split-K as a strided batched GEMM.
+    """
+
+    KC = 2048      # split-K chunk (rows of B*n per partial product)
+
+    @staticmethod
+    def forward(ctx, h2d, w, b):
+        n_W, L, H = w.shape
+        BN = h2d.shape[0]
+        hid3 = h2d.view(BN, n_W, H).permute(1, 0, 2)                     # [n_W, BN, H] strided view
+        out = torch.baddbmm(b.unsqueeze(-1), w, hid3.transpose(1, 2))     # [n_W, L, BN]
+        ctx.save_for_backward(h2d, w)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dout):
+        h2d, w = ctx.saved_tensors
+        n_W, L, H = w.shape
+        BN = h2d.shape[0]
+        dout = dout.contiguous()
+        dh = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dh = torch.empty_like(h2d)
+            dh3 = dh.view(BN, n_W, H)
+            for m in range(n_W):                                          # [BN, L] @ [L, H] -> strided slice
+                torch.mm(dout[m].t(), w[m], out=dh3[:, m, :])
+        if ctx.needs_input_grad[1]:
+            kc = _TapMajorLastLinear.KC
+            while BN % kc:
+                kc //= 2
+            S = BN // kc
+            h4 = h2d.view(S, kc, n_W, H)
+            dw = torch.empty_like(w)
+            for m in range(n_W):
+                a = dout[m].view(L, S, kc).permute(1, 0, 2)               # [S, L, kc]
+                part = torch.bmm(a, h4[:, :, m, :])                       # [S, L, H]
+                torch.sum(part, dim=0, out=dw[m])
+        if ctx.needs_input_grad[2]:
+            db = dout.sum(-1)
+        return dh, dw, db
+
+
 def generate_factors(fs: Sequence[MLPBlock], data: torch.Tensor) -> torch.Tensor:
     """``W[m] = fs[m](data)`` for every m (psf.py:175), computed as batched GEMMs.
 
@@ -109,32 +161,35 @@ def generate_factors(fs: Sequence[MLPBlock], data: torch.Tensor) -> torch.Tensor
     if not _same_structure(fs):
         # heterogeneous generators: evaluate one by one (reference order), then re-lay
         return torch.stack([f(data) for f in fs], 0)
-    x = None          # [n_W, B*n, width] once the generators have diverged
+    # activations of all generators side by side: [B*n, n_W*width] contiguous, so that elementwise
+    # layers run on a dense buffer; None while the generators still share their input
+    h2d = None
+    width = E
     layers = list(zip(*[list(f.network) for f in fs]))
     last_linear = max(i for i, ls in enumerate(layers) if isinstance(ls[0], nn.Linear))
     for i, ls in enumerate(layers):
         if isinstance(ls[0], nn.GELU):
-            if x is None:      # GELU straight on the shared input
+            if h2d is None:
                 x_shared = F.gelu(x_shared)
             else:
-                x = F.gelu(x)
+                h2d = F.gelu(h2d)
             continue
         w = torch.stack([l.weight for l in ls], 0)                 # [n_W, out, in]
         bvec = torch.stack([l.bias for l in ls], 0)                # [n_W, out]
         out_f = w.shape[1]
         if i == last_linear:
-            if x is None:
-                xt = x_shared.t().unsqueeze(0).expand(n_W, -1, -1)   # [n_W, in, B*n]
-            else:
-                xt = x.transpose(1, 2)
-            wt = torch.baddbmm(bvec.unsqueeze(-1), w, xt)          # [n_W, L, B*n]
+            if h2d is None:                                        # no hidden layer at all
+                h2d = x_shared.repeat(1, n_W)
+            wt = _TapMajorLastLinear.apply(h2d, w, bvec)           # [n_W, L, B*n]
             return wt.view(n_W, out_f, B, n).permute(0, 2, 3, 1)   # logical [n_W, B, n, L]
-        if x is None:
+        if h2d is None:
             # one GEMM for all generators: [B*n, in] x [in, n_W*out]
-            h = torch.addmm(bvec.reshape(-1), x_shared, w.reshape(n_W * out_f, -1).t())
-            x = h.view(B * n, n_W, out_f).permute(1, 0, 2)         # [n_W, B*n, out], no copy
+            h2d = torch.addmm(bvec.reshape(-1), x_shared, w.reshape(n_W * out_f, -1).t())
         else:
-            x = torch.baddbmm(bvec.unsqueeze(1), x, w.transpose(1, 2))
+            x3 = h2d.view(B * n, n_W, width).permute(1, 0, 2)      # [n_W, B*n, width]
+            y3 = torch.baddbmm(bvec.unsqueeze(1), x3, w.transpose(1, 2))
+            h2d = y3.permute(1, 0, 2).reshape(B * n, n_W * out_f)
+        width = out_f
     raise RuntimeError("generator has no Linear layer")
 
 
