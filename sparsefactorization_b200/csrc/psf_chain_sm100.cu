@@ -102,6 +102,24 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint3
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// same, with an L2 evict-first policy: W is streamed once, it must not push the exchanged states out of L2
+__device__ __forceinline__ void tma_load_1d_stream(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
+                                                   unsigned long long policy) {
+  if (policy == 0) {
+    tma_load_1d(dst, src, bytes, bar);
+    return;
+  }
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ unsigned long long make_evict_first_policy() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -261,6 +279,7 @@ struct Producer {
   uint32_t ph;         // empty-barrier parity to test (1 on a fresh barrier)
   int ahead;           // stages issued and not yet consumed by warp 0
   bool valid;
+  unsigned long long policy;  // L2 evict-first policy for the W stream
 };
 
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
@@ -286,6 +305,7 @@ __device__ __forceinline__ void producer_init(Producer& pr, const FusedParams& p
   pr.ph = 1u;
   pr.ahead = 0;
   pr.valid = (pr.b < p.B) && (g.npass > 0);
+  pr.policy = (p.dbg & 64) ? 0ull : make_evict_first_policy();
 }
 
 // Issue the stage under the cursor (lane 0 of warp 0 only) and advance the cursor (all lanes).
@@ -305,7 +325,8 @@ __device__ __forceinline__ void producer_issue(Producer& pr, const FusedParams& 
       mbar_expect_tx(bar, bytes * (uint32_t)kn);
 #pragma unroll
       for (int t = 0; t < kTps; ++t)
-        if (t < kn) tma_load_1d(dst + (uint32_t)(t * sm.slot) * 4u, wfac + sm.tapoff[i0 + t] + row0, bytes, bar);
+        if (t < kn)
+          tma_load_1d_stream(dst + (uint32_t)(t * sm.slot) * 4u, wfac + sm.tapoff[i0 + t] + row0, bytes, bar, pr.policy);
     } else {
       uint32_t total = 0;
 #pragma unroll
@@ -323,8 +344,9 @@ __device__ __forceinline__ void producer_issue(Producer& pr, const FusedParams& 
           const int first = min(len, p.n - a0);      // part before the cyclic wrap
           const float* wk = wfac + sm.tapoff[i0 + t];
           const uint32_t d = dst + (uint32_t)(t * sm.slot) * 4u;
-          tma_load_1d(d, wk + a0, (uint32_t)first * 4u, bar);
-          if (first < len) tma_load_1d(d + (uint32_t)first * 4u, wk, (uint32_t)(len - first) * 4u, bar);
+          tma_load_1d_stream(d, wk + a0, (uint32_t)first * 4u, bar, pr.policy);
+          if (first < len)
+            tma_load_1d_stream(d + (uint32_t)first * 4u, wk, (uint32_t)(len - first) * 4u, bar, pr.policy);
         }
       }
     }
@@ -419,6 +441,7 @@ __global__ void __launch_bounds__(kMaxThreads, (kPlane <= 2048 ? 2 : 1)) psf_cha
   const long long plane = (long long)CT * n;  // floats per sample per state
   int slot = 0;
   uint32_t parity = 0, vparity = 0;
+  bool cw_pending = false;  // arrived on the cluster barrier, wait deferred to the first use of exchanged data
   const bool refresher = (threadIdx.x == 0);
 
   for (int b = g.cid; b < p.B; b += g.ncl) {
@@ -437,7 +460,11 @@ __global__ void __launch_bounds__(kMaxThreads, (kPlane <= 2048 ? 2 : 1)) psf_cha
     consumer_bar_sync(nthr_c);  // the block is written; nobody reads the shared copy any more
     if (refresher) refresh_state<kPlane>(sm, g, st0, n);
     cluster_arrive();
-    cluster_wait();
+    cw_pending = true;
+    if (p.dbg & 128) {
+      cluster_wait();
+      cw_pending = false;
+    }
 
     for (int m = 1; m <= p.n_W; ++m) {
       // slot 0 always keeps V_0 (residual operand); without saved states slots 1/2 alternate
@@ -474,8 +501,14 @@ __global__ void __launch_bounds__(kMaxThreads, (kPlane <= 2048 ? 2 : 1)) psf_cha
             mbar_wait(sm.full_u32 + slot * 8, parity);
           }
           const float* wst = sm.ring + slot * sm.stage_f + g.warp * kTile + 4 * g.lane;
-          if (mine) {
-            if (tg == 0 && p.head) {
+          // The deferred cluster wait must be executed by whole warps: decide it from warp-uniform values
+          // (tile origin, tap offset) - does any row of this tile reach past the block with this tap?
+          if (tg == 0 && p.head) {
+            if (cw_pending && row0 + kTile + 8 > g.blk_end) {
+              cluster_wait();
+              cw_pending = false;
+            }
+            if (mine) {
               // taps with offsets 0,1,2,4 share the quads A = rows j..j+3 and Bq = rows j+4..j+7
               const float4 w0 = lds4(wst), w1 = lds4(wst + sm.slot), w2 = lds4(wst + 2 * sm.slot),
                            w3 = lds4(wst + 3 * sm.slot);
@@ -495,13 +528,19 @@ __global__ void __launch_bounds__(kMaxThreads, (kPlane <= 2048 ? 2 : 1)) psf_cha
                 acc[ch].z = fmaf(w1.z, A.w, acc[ch].z);
                 acc[ch].w = fmaf(w1.w, Bq.x, acc[ch].w);
               }
-            } else {
+            }
+          } else {
 #pragma unroll
-              for (int t = 0; t < kTps; ++t) {
-                const int i = tg * kTps + t;
-                if (i < p.L) {
+            for (int t = 0; t < kTps; ++t) {
+              const int i = tg * kTps + t;
+              if (i < p.L) {
+                const int o = sm.offs[i];
+                if (cw_pending && row0 + kTile + 8 + o > g.blk_end) {
+                  cluster_wait();
+                  cw_pending = false;
+                }
+                if (mine) {
                   const float4 w4 = lds4(wst + t * sm.slot);
-                  const int o = sm.offs[i];
                   const int src = j + o;
                   if ((o & 3) == 0) {
                     if (src + 4 <= g.blk_end || (p.dbg & 4)) {
@@ -553,6 +592,10 @@ __global__ void __launch_bounds__(kMaxThreads, (kPlane <= 2048 ? 2 : 1)) psf_cha
             }
           }
         }
+        if (cw_pending) {  // at the latest before this CTA publishes V_m (state slots may be reused)
+          cluster_wait();
+          cw_pending = false;
+        }
         if (mine) {
           if (pend) {
 #pragma unroll
@@ -575,8 +618,12 @@ __global__ void __launch_bounds__(kMaxThreads, (kPlane <= 2048 ? 2 : 1)) psf_cha
           if (p.dbg & 16) mbar_arrive(sm.vbar_u32); else refresh_state<kPlane>(sm, g, next, n);
         }
         if (!(p.dbg & 2)) {
-          cluster_arrive();           // V_m visible cluster-wide
-          cluster_wait();
+          cluster_arrive();           // V_m visible cluster-wide once the (deferred) wait returns
+          cw_pending = true;
+          if (p.dbg & 128) {
+            cluster_wait();
+            cw_pending = false;
+          }
         }
       }
     }
@@ -607,12 +654,15 @@ __global__ void __launch_bounds__(kMaxThreads, (kPlane <= 2048 ? 2 : 1)) psf_cha
   const long long plane = (long long)CT * n;
   int slot = 0;
   uint32_t parity = 0, vparity = 0;
+  bool cw_pending = false;  // arrived on the cluster barrier, wait deferred to the first use of exchanged data
   const bool refresher = (threadIdx.x == 0);
 
   for (int b = g.cid; b < p.B; b += g.ncl) {
-    float* gx0 = p.gx + (long long)b * plane;          // exchange slot 0
-    float* gx1 = p.gx + ((long long)p.B + b) * plane;  // exchange slot 1
-    float* racc = p.racc + (long long)b * plane;
+    // exchange / residual buffers are per CLUSTER (reused sample after sample): 3 x 0.5 MB x 33 clusters
+    // stays L2 resident, whereas per-sample buffers were written back to HBM once per factor
+    float* gx0 = p.gx + (long long)g.cid * plane;            // exchange slot 0
+    float* gx1 = p.gx + ((long long)g.ncl + g.cid) * plane;  // exchange slot 1
+    float* racc = p.racc + (long long)g.cid * plane;
     // ---- prologue: dOut block -> exchange slot 0 (channel-major) ---------------------------
     for (int pp = 0; pp < g.npass; ++pp) {
       const int j = g.blk_start + (pp * g.ncw + g.warp) * kTile + 4 * g.lane;
@@ -627,7 +677,11 @@ __global__ void __launch_bounds__(kMaxThreads, (kPlane <= 2048 ? 2 : 1)) psf_cha
     consumer_bar_sync(nthr_c);
     if (refresher) refresh_state<kPlane>(sm, g, gx0, n);
     cluster_arrive();
-    cluster_wait();
+    cw_pending = true;
+    if (p.dbg & 128) {
+      cluster_wait();
+      cw_pending = false;
+    }
 
     for (int m = p.n_W; m >= 1; --m) {
       const int step = p.n_W - m;
@@ -658,12 +712,18 @@ __global__ void __launch_bounds__(kMaxThreads, (kPlane <= 2048 ? 2 : 1)) psf_cha
           if (g.warp == 0 && pr.ahead == 0) producer_pump<true, kTps>(pr, p, g, sm, true);
           mbar_wait(sm.full_u32 + slot * 8, parity);
           const float* wst = sm.ring + slot * sm.stage_f + g.warp * kTile + 4 * g.lane;
-          if (mine) {
+          {
 #pragma unroll
             for (int t = 0; t < kTps; ++t) {
               const int i = tg * kTps + t;
               if (i < p.L) {
                 const int o = sm.offs[i];
+                // deferred cluster wait, decided from warp-uniform values (whole warps must execute it)
+                if (cw_pending && row0 - o - 8 < g.blk_start) {
+                  cluster_wait();
+                  cw_pending = false;
+                }
+                if (!mine) continue;
                 const int src = j - o;  // first source row (may be negative: cyclic)
                 float* dwk = dwbase + sm.tapoff[i];
                 if ((o & 3) == 0) {
@@ -729,6 +789,10 @@ __global__ void __launch_bounds__(kMaxThreads, (kPlane <= 2048 ? 2 : 1)) psf_cha
             producer_pump<true, kTps>(pr, p, g, sm, false);
           }
         }
+        if (cw_pending) {
+          cluster_wait();
+          cw_pending = false;
+        }
         if (mine) {
           // residual: dV0 also receives G_m of every factor (V_m = W_m V_{m-1} + V_0)
           if (p.residual) {
@@ -756,9 +820,17 @@ __global__ void __launch_bounds__(kMaxThreads, (kPlane <= 2048 ? 2 : 1)) psf_cha
         consumer_bar_sync(nthr_c);
         if (refresher) refresh_state<kPlane>(sm, g, gnext, n);
         cluster_arrive();
-        cluster_wait();
+        cw_pending = true;
+        if (p.dbg & 128) {
+          cluster_wait();
+          cw_pending = false;
+        }
       }
     }
+    // the exchange buffers belong to the cluster: the next sample may overwrite them only after every
+    // CTA has finished reading this sample's last state
+    cluster_arrive();
+    cluster_wait();
   }
 }
 
@@ -866,11 +938,11 @@ void make_order(const PsfChainArgs& a, bool backward, int* order, int* head) {
   const int nb = (nr + 3) / 4;
   int lo = 0, hi = nr - 1, bigs = 0;
   while (lo <= hi) {
-    if (bigs < nb) {
+    for (int q = 0; q < 3 && lo <= hi; ++q) order[pos++] = rest[lo++];
+    if (bigs < nb && lo <= hi) {
       order[pos++] = rest[hi--];
       ++bigs;
     }
-    for (int q = 0; q < 3 && lo <= hi; ++q) order[pos++] = rest[lo++];
   }
 }
 
