@@ -64,6 +64,10 @@ def cpu_oracle_seqs_per_sec(batch, steps, warmup):
     import torch
     import oracle
     from sparsefactorization_b200 import data
+    try:        # all the host threads this process may use (torchrun pins OMP_NUM_THREADS to 1)
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, RuntimeError):
+        pass
     torch.manual_seed(42)
     kw = psf_kwargs(False)
     net = oracle.OraclePSFNet("synthetic", **kw)

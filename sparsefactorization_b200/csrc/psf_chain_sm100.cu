@@ -44,9 +44,12 @@ constexpr int kMaxStages = 8;  // W ring depth is a launch parameter
 constexpr int kMaxThreads = kMaxCW * 32;
 
 // ring geometry: forward stages 4 taps (the {0,1,2,4} head group is one stage); backward stages
-// 3 taps whose per-tap windows carry 8 spare floats (16 B aligned, shifted source windows).
+// single taps whose windows carry 8 spare floats (16 B aligned, shifted source windows).
 constexpr int kTpsF = 4;
-constexpr int kTpsB = 3;
+#ifndef PSF_TPS_B
+#define PSF_TPS_B 4
+#endif
+constexpr int kTpsB = PSF_TPS_B;  // 4 taps x 2 stages measured best; 1-tap stages with deep rings and 5-tap stages are slower
 constexpr int kPadB = 8;
 
 struct FusedParams {
@@ -61,7 +64,7 @@ struct FusedParams {
   int B, n, n_W, L, residual, save_states;
   int P, RB;
   int head;           // fwd: visits 0..3 are the taps with offsets 0,1,2,4
-  int stages;         // W ring depth
+  int stages;         // W ring depth (of the kernel being launched)
   int ncw;            // warps per CTA (warp 0 / lane 0 also streams W)
   int dbg;            // timing experiments only (PSF_FUSED_DEBUG): 1 no state stores, 2 no cluster barrier,
                       // 4 all taps local, 8 no W stream, 16 no state refresh, 32 no residual
@@ -278,7 +281,7 @@ struct Producer {
   int slot;            // ring slot it goes to
   uint32_t ph;         // empty-barrier parity to test (1 on a fresh barrier)
   int ahead;           // stages issued and not yet consumed by warp 0
-  bool valid;
+  int valid;
   unsigned long long policy;  // L2 evict-first policy for the W stream
 };
 
@@ -304,7 +307,7 @@ __device__ __forceinline__ void producer_init(Producer& pr, const FusedParams& p
   pr.slot = 0;
   pr.ph = 1u;
   pr.ahead = 0;
-  pr.valid = (pr.b < p.B) && (g.npass > 0);
+  pr.valid = ((pr.b < p.B) && (g.npass > 0)) ? 1 : 0;
   pr.policy = (p.dbg & 64) ? 0ull : make_evict_first_policy();
 }
 
@@ -363,7 +366,7 @@ __device__ __forceinline__ void producer_issue(Producer& pr, const FusedParams& 
       if (++pr.mm == p.n_W) {
         pr.mm = 0;
         pr.b += g.ncl;
-        pr.valid = pr.b < p.B;
+        pr.valid = pr.b < p.B ? 1 : 0;
       }
     }
   }
@@ -431,8 +434,10 @@ __global__ void __launch_bounds__(kMaxThreads, (kPlane <= 2048 ? 2 : 1)) psf_cha
   init_barriers(p, sm);
 
   Producer pr;
-  producer_init(pr, p, g);
-  if (g.warp == 0 && !(p.dbg & 8)) producer_pump<false, kTps>(pr, p, g, sm, false);
+  if (g.warp == 0) {
+    producer_init(pr, p, g);
+    if (!(p.dbg & 8)) producer_pump<false, kTps>(pr, p, g, sm, false);
+  }
 
   const int S = p.stages;
   const int nthr_c = g.ncw * 32;
@@ -485,15 +490,6 @@ __global__ void __launch_bounds__(kMaxThreads, (kPlane <= 2048 ? 2 : 1)) psf_cha
 #pragma unroll
         for (int ch = 0; ch < CT; ++ch) acc[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-        // one global-operand tap in flight: issued here, consumed after the next local taps
-        bool pend = false;
-        float4 pw = make_float4(1.f, 1.f, 1.f, 1.f);
-        float4 pv[CT];
-        if (mine && p.residual && !(p.dbg & 32)) {  // the residual V_0 rides the pending slot with weight 1
-#pragma unroll
-          for (int ch = 0; ch < CT; ++ch) pv[ch] = ld_cg4(st0 + ch * n + j);
-          pend = true;
-        }
         const float* vown = Vs + (j - g.blk_start);
         for (int tg = 0; tg < g.ngroups; ++tg) {
           if (!(p.dbg & 8)) {
@@ -551,15 +547,12 @@ __global__ void __launch_bounds__(kMaxThreads, (kPlane <= 2048 ? 2 : 1)) psf_cha
 #pragma unroll
                       for (int ch = 0; ch < CT; ++ch) fma4(acc[ch], w4, v[ch]);
                     } else {
-                      if (pend) {
-#pragma unroll
-                        for (int ch = 0; ch < CT; ++ch) fma4(acc[ch], pw, pv[ch]);
-                      }
                       const float* gp = prev + (src >= n ? src - n : src);
-                      pw = w4;
+                      float4 v[CT];
 #pragma unroll
-                      for (int ch = 0; ch < CT; ++ch) pv[ch] = ld_cg4(gp + ch * n);
-                      pend = true;
+                      for (int ch = 0; ch < CT; ++ch) v[ch] = ld_cg4(gp + ch * n);
+#pragma unroll
+                      for (int ch = 0; ch < CT; ++ch) fma4(acc[ch], w4, v[ch]);
                     }
                   } else {
                     // unaligned tap: the two aligned quads covering rows src..src+3, select in registers
@@ -597,9 +590,9 @@ __global__ void __launch_bounds__(kMaxThreads, (kPlane <= 2048 ? 2 : 1)) psf_cha
           cw_pending = false;
         }
         if (mine) {
-          if (pend) {
+          if (p.residual) {
 #pragma unroll
-            for (int ch = 0; ch < CT; ++ch) fma4(acc[ch], pw, pv[ch]);
+            for (int ch = 0; ch < CT; ++ch) add4(acc[ch], ld_cg4(st0 + ch * n + j));
           }
           if (!last) {
             if (!(p.dbg & 1) || acc[0].x == 123.456f) {
@@ -644,8 +637,10 @@ __global__ void __launch_bounds__(kMaxThreads, (kPlane <= 2048 ? 2 : 1)) psf_cha
   init_barriers(p, sm);
 
   Producer pr;
-  producer_init(pr, p, g);
-  if (g.warp == 0) producer_pump<true, kTps>(pr, p, g, sm, false);
+  if (g.warp == 0) {
+    producer_init(pr, p, g);
+    producer_pump<true, kTps>(pr, p, g, sm, false);
+  }
 
   const int S = p.stages;
   const int nthr_c = g.ncw * 32;
@@ -839,7 +834,7 @@ __global__ void __launch_bounds__(kMaxThreads, (kPlane <= 2048 ? 2 : 1)) psf_cha
 // ---------------------------------------------------------------------------------------------
 int plane_for(int RB) { return RB <= 512 ? 512 : (RB <= 2048 ? 2048 : 4096); }
 
-int smem_bytes_for(int RB, int ncw, int stages, bool backward) {
+int smem_bytes_for(int RB, int ncw, int stages, bool backward) {  // stages of THAT kernel
   const int slot = ncw * kTile + (backward ? kPadB : 0);
   const int ring = stages * (backward ? kTpsB : kTpsF) * slot;
   return CT * plane_for(RB) * 4 + ring * 4 + (2 * stages + 2) * 8 + PSF_MAX_TAPS * 12;
@@ -974,7 +969,7 @@ void fill_common(FusedParams& fp, const PsfChainArgs& a, const PsfFusedPlan& pla
   fp.residual = a.residual;
   fp.P = plan.cluster;
   fp.RB = plan.rows_per_cta;
-  fp.stages = plan.stages;
+  fp.stages = backward ? plan.stages_bwd : plan.stages;
   fp.ncw = plan.threads / 32;
   fp.dbg = env_int("PSF_FUSED_DEBUG", 0);
   int order[PSF_MAX_TAPS];
@@ -1013,17 +1008,25 @@ int psf_fused_plan(const PsfChainArgs& a, PsfFusedPlan* plan) {
   if (ncw > max_cw) ncw = max_cw;
   if (ncw > kMaxCW) ncw = kMaxCW;
   const int threads = ncw * 32;
-  int stages = env_int("PSF_FUSED_STAGES", 3);
+  // two stages: the smaller ring leaves ~36 KB of L1 per SM (spill traffic otherwise goes to L2); deeper rings
+  // measured slower (tools/knob_sweep.sh)
+  int stages = env_int("PSF_FUSED_STAGES", 2);
+  int stages_b = env_int("PSF_FUSED_STAGES_BWD", 2);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
-  while (stages > 2 && smem_bytes_for(RB, ncw, stages, true) > 227 * 1024) --stages;
-  if (smem_bytes_for(RB, ncw, stages, true) > 227 * 1024) return PSF_ERR_UNSUPPORTED;
+  if (stages_b > kMaxStages) stages_b = kMaxStages;
+  if (stages_b < 2) stages_b = 2;
+  while (stages > 2 && smem_bytes_for(RB, ncw, stages, false) > 227 * 1024) --stages;
+  while (stages_b > 2 && smem_bytes_for(RB, ncw, stages_b, true) > 227 * 1024) --stages_b;
+  if (smem_bytes_for(RB, ncw, stages, false) > 227 * 1024 || smem_bytes_for(RB, ncw, stages_b, true) > 227 * 1024)
+    return PSF_ERR_UNSUPPORTED;
   plan->cluster = P;
   plan->rows_per_cta = RB;
   plan->threads = threads;
   plan->stages = stages;
+  plan->stages_bwd = stages_b;
   plan->smem_bytes = smem_bytes_for(RB, ncw, stages, false);
-  plan->smem_bytes_bwd = smem_bytes_for(RB, ncw, stages, true);
+  plan->smem_bytes_bwd = smem_bytes_for(RB, ncw, stages_b, true);
 
   if (!g_attr_done) {
     const int planes[3] = {512, 2048, 4096};

@@ -57,7 +57,8 @@ struct PsfFusedPlan {
   int resident;       // clusters that fit on the device at once, forward kernel
   int smem_bytes_bwd; // same for the backward kernel (different W ring geometry)
   int resident_bwd;
-  int stages;         // W ring depth per warp
+  int stages;         // W ring depth, forward kernel
+  int stages_bwd;     // W ring depth, backward kernel
 };
 int psf_fused_plan(const PsfChainArgs& a, PsfFusedPlan* plan);   // PSF_OK or PSF_ERR_UNSUPPORTED
 bool psf_fused_buffers_ok(const PsfChainArgs& a, const void* W, const void* p1, const void* p2, const void* ws);
