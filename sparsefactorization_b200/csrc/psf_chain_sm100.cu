@@ -14,10 +14,10 @@
 //     read straight from the previous state in global memory (written by the sibling CTAs one
 //     factor earlier); one hardware cluster barrier (release/acquire) per factor orders it.
 //   * W STREAM.  W is read exactly once, tap-major ([..][tap][row], row stride 1): the rows a pass
-//     covers (consumer warps x 128) are one contiguous run per tap.  A dedicated producer warp
-//     issues cp.async.bulk (TMA 1-D, up to 4 KB each) into a CTA-shared ring of stages guarded by
-//     full/empty mbarriers; consumer warps never touch pointers into W.  Chord offsets are
-//     arithmetic, there are no COO index gathers anywhere.
+//     covers (warps x 128) are one contiguous run per tap, fetched with cp.async.bulk (TMA 1-D, 4 KB
+//     each, L2 evict-first) into a CTA-shared ring of stages.  Consumers wait on a per-slot mbarrier;
+//     the warp that releases a slot last (release counter) issues the slot's next stage at once.
+//     Chord offsets are arithmetic, there are no COO index gathers anywhere.
 //   * MATH.  Every consumer thread owns 4 consecutive rows x 8 channels: all shared/global
 //     operand accesses are 128-bit and bank-conflict free, FMAs are packed fma.rn.f32x2.  Taps
 //     whose offset is not a multiple of 4 read the two aligned quads that cover them; in the
@@ -245,7 +245,8 @@ __device__ __forceinline__ void make_geom(Geom& g, const FusedParams& p, int tps
 //   then mbarriers: full[stages], empty[stages], vbar
 struct Smem {
   float* state;
-  uint32_t ring_u32, full_u32, empty_u32, vbar_u32, state_u32;
+  uint32_t ring_u32, full_u32, vbar_u32, state_u32;
+  int* relcnt;     // [stages] warps that have released each ring slot
   const float* ring;
   int slot;        // floats per tap window
   int stage_f;     // floats per stage
@@ -263,126 +264,85 @@ __device__ __forceinline__ void carve(Smem& sm, unsigned char* raw, const FusedP
   sm.state_u32 = smem_u32(sm.state);
   sm.ring_u32 = smem_u32(ring);
   sm.full_u32 = sm.ring_u32 + (uint32_t)(p.stages * sm.stage_f) * 4u;
-  sm.empty_u32 = sm.full_u32 + (uint32_t)p.stages * 8u;
-  sm.vbar_u32 = sm.empty_u32 + (uint32_t)p.stages * 8u;
+  sm.vbar_u32 = sm.full_u32 + (uint32_t)p.stages * 8u;
+  sm.relcnt = reinterpret_cast<int*>(ring + p.stages * sm.stage_f) + 2 * (p.stages + 1);
   unsigned char* tab = reinterpret_cast<unsigned char*>(ring + p.stages * sm.stage_f) + (2 * p.stages + 2) * 8;
   sm.tapoff = reinterpret_cast<const long long*>(tab);
   sm.offs = reinterpret_cast<const int*>(tab + PSF_MAX_TAPS * 8);
 }
 
 // ---------------------------------------------------------------------------------------------
-// W producer.  Warp 0 carries a cursor over every (sample, factor, pass, tap group) of this CTA, in
-// the exact order the stages are consumed; at each stage boundary its lane 0 tops the ring up with
-// whatever slots every warp has released (non-blocking test of the empty barrier), and only blocks
-// if the stage it is about to consume itself has not been issued yet.
+// W stream.  Every stage of this CTA has an index gidx = ((sample_iteration * n_W + factor_step) * npass
+// + pass) * ngroups + tap_group, consumed in increasing order by all warps.  There is no producer warp
+// and no cursor: the warp that releases a ring slot LAST (per-slot release counter) immediately issues
+// the stage that goes into that slot next, gidx + stages, decoding the index arithmetically.
 // ---------------------------------------------------------------------------------------------
-struct Producer {
-  int b, mm, pp, tg;   // next stage to issue
-  int slot;            // ring slot it goes to
-  uint32_t ph;         // empty-barrier parity to test (1 on a fresh barrier)
-  int ahead;           // stages issued and not yet consumed by warp 0
-  int valid;
-  unsigned long long policy;  // L2 evict-first policy for the W stream
-};
-
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-
-__device__ __forceinline__ void producer_init(Producer& pr, const FusedParams& p, const Geom& g) {
-  pr.b = g.cid;
-  pr.mm = 0;
-  pr.pp = 0;
-  pr.tg = 0;
-  pr.slot = 0;
-  pr.ph = 1u;
-  pr.ahead = 0;
-  pr.valid = ((pr.b < p.B) && (g.npass > 0)) ? 1 : 0;
-  pr.policy = (p.dbg & 64) ? 0ull : make_evict_first_policy();
-}
-
-// Issue the stage under the cursor (lane 0 of warp 0 only) and advance the cursor (all lanes).
 template <bool kBackward, int kTps>
-__device__ __forceinline__ void producer_issue(Producer& pr, const FusedParams& p, const Geom& g, const Smem& sm) {
-  if (g.lane == 0) {
-    const int m = kBackward ? p.n_W - pr.mm : pr.mm + 1;
-    const float* wfac = p.W + (long long)(m - 1) * p.sWf + (long long)pr.b * p.sWb;
-    const int row0 = g.blk_start + pr.pp * g.prows;
-    const int prow = min(g.prows, g.blk_end - row0);
-    const uint32_t bar = sm.full_u32 + pr.slot * 8;
-    const uint32_t dst = sm.ring_u32 + (uint32_t)(pr.slot * sm.stage_f) * 4u;
-    const int i0 = pr.tg * kTps;
-    if (!kBackward) {
-      const int kn = min(kTps, p.L - i0);
-      const uint32_t bytes = (uint32_t)prow * 4u;
-      mbar_expect_tx(bar, bytes * (uint32_t)kn);
-#pragma unroll
-      for (int t = 0; t < kTps; ++t)
-        if (t < kn)
-          tma_load_1d_stream(dst + (uint32_t)(t * sm.slot) * 4u, wfac + sm.tapoff[i0 + t] + row0, bytes, bar, pr.policy);
-    } else {
-      uint32_t total = 0;
-#pragma unroll
-      for (int t = 0; t < kTps; ++t)
-        if (i0 + t < p.L) total += (uint32_t)(prow + ((sm.offs[i0 + t] & 3) ? 4 : 0)) * 4u;
-      mbar_expect_tx(bar, total);
-#pragma unroll
-      for (int t = 0; t < kTps; ++t) {
-        if (i0 + t < p.L) {
-          const int o = sm.offs[i0 + t];
-          int s0 = row0 - o;
-          if (s0 < 0) s0 += p.n;
-          const int a0 = s0 & ~3;                    // 16 B aligned start of the source window
-          const int len = prow + ((o & 3) ? 4 : 0);  // floats
-          const int first = min(len, p.n - a0);      // part before the cyclic wrap
-          const float* wk = wfac + sm.tapoff[i0 + t];
-          const uint32_t d = dst + (uint32_t)(t * sm.slot) * 4u;
-          tma_load_1d_stream(d, wk + a0, (uint32_t)first * 4u, bar, pr.policy);
-          if (first < len)
-            tma_load_1d_stream(d + (uint32_t)first * 4u, wk, (uint32_t)(len - first) * 4u, bar, pr.policy);
-        }
-      }
-    }
+__device__ __forceinline__ void issue_stage_index(int gidx, int slot, const FusedParams& p, const Geom& g,
+                                                  const Smem& sm) {
+  const int spp = g.ngroups;        // stages per pass
+  const int sps = spp * g.npass;    // stages per factor step
+  const int spsample = sps * p.n_W;
+  if (spsample == 0) return;
+  const int it = gidx / spsample;   // which of this cluster's samples
+  const int b = g.cid + it * g.ncl;
+  if (b >= p.B) return;
+  int r = gidx - it * spsample;
+  const int mm = r / sps;
+  r -= mm * sps;
+  const int pp = r / spp;
+  const int tg = r - pp * spp;
+  const unsigned long long policy = (p.dbg & 64) ? 0ull : make_evict_first_policy();
+  const int m = kBackward ? p.n_W - mm : mm + 1;
+  const float* wfac = p.W + (long long)(m - 1) * p.sWf + (long long)b * p.sWb;
+  const int row0 = g.blk_start + pp * g.prows;
+  const int prow = min(g.prows, g.blk_end - row0);
+  const uint32_t bar = sm.full_u32 + slot * 8;
+  const uint32_t dst = sm.ring_u32 + (uint32_t)(slot * sm.stage_f) * 4u;
+  const int i0 = tg * kTps;
+  if (prow <= 0) {  // nothing to stream for this pass (cannot happen for non-empty blocks): complete the phase
+    mbar_arrive(bar);
+    return;
   }
-  ++pr.ahead;
-  if (++pr.slot == p.stages) {
-    pr.slot = 0;
-    pr.ph ^= 1u;
-  }
-  if (++pr.tg == g.ngroups) {
-    pr.tg = 0;
-    if (++pr.pp == g.npass) {
-      pr.pp = 0;
-      if (++pr.mm == p.n_W) {
-        pr.mm = 0;
-        pr.b += g.ncl;
-        pr.valid = pr.b < p.B ? 1 : 0;
+  if (!kBackward) {
+    const int kn = min(kTps, p.L - i0);
+    const uint32_t bytes = (uint32_t)prow * 4u;
+    mbar_expect_tx(bar, bytes * (uint32_t)kn);
+#pragma unroll
+    for (int t = 0; t < kTps; ++t)
+      if (t < kn)
+        tma_load_1d_stream(dst + (uint32_t)(t * sm.slot) * 4u, wfac + sm.tapoff[i0 + t] + row0, bytes, bar, policy);
+  } else {
+    uint32_t total = 0;
+#pragma unroll
+    for (int t = 0; t < kTps; ++t)
+      if (i0 + t < p.L) total += (uint32_t)(prow + ((sm.offs[i0 + t] & 3) ? 4 : 0)) * 4u;
+    mbar_expect_tx(bar, total);
+#pragma unroll
+    for (int t = 0; t < kTps; ++t) {
+      if (i0 + t < p.L) {
+        const int o = sm.offs[i0 + t];
+        int s0 = row0 - o;
+        if (s0 < 0) s0 += p.n;
+        const int a0 = s0 & ~3;                    // 16 B aligned start of the source window
+        const int len = prow + ((o & 3) ? 4 : 0);  // floats
+        const int first = min(len, p.n - a0);      // part before the cyclic wrap
+        const float* wk = wfac + sm.tapoff[i0 + t];
+        const uint32_t d = dst + (uint32_t)(t * sm.slot) * 4u;
+        tma_load_1d_stream(d, wk + a0, (uint32_t)first * 4u, bar, policy);
+        if (first < len) tma_load_1d_stream(d + (uint32_t)first * 4u, wk, (uint32_t)(len - first) * 4u, bar, policy);
       }
     }
   }
 }
 
-// Top the ring up.  must_have: warp 0 is about to consume a stage, so at least one must be in flight.
+// Called by lane 0 of every warp when the warp is done with stage `gs` in `slot`.
 template <bool kBackward, int kTps>
-__device__ __forceinline__ void producer_pump(Producer& pr, const FusedParams& p, const Geom& g, const Smem& sm,
-                                              bool must_have) {
-  while (pr.valid && pr.ahead < p.stages) {
-    const uint32_t bar = sm.empty_u32 + pr.slot * 8;
-    if (!mbar_test(bar, pr.ph)) {
-      if (!(must_have && pr.ahead == 0)) break;
-      mbar_wait(bar, pr.ph);
-    }
-    producer_issue<kBackward, kTps>(pr, p, g, sm);
+__device__ __forceinline__ void release_stage(int gs, int slot, const FusedParams& p, const Geom& g, const Smem& sm) {
+  int* cnt = sm.relcnt + slot;
+  if (atomicAdd(cnt, 1) == g.ncw - 1) {   // last warp out refills the slot
+    *cnt = 0;                              // ordered before the consumers' next use by the release in expect_tx
+    issue_stage_index<kBackward, kTps>(gs + p.stages, slot, p, g, sm);
   }
 }
 
@@ -412,7 +372,7 @@ __device__ __forceinline__ void init_barriers(const FusedParams& p, const Smem& 
     }
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(sm.full_u32 + s * 8, 1);
-      mbar_init(sm.empty_u32 + s * 8, (uint32_t)p.ncw);
+      sm.relcnt[s] = 0;
     }
     mbar_init(sm.vbar_u32, 1);
     fence_barrier_init();
@@ -433,11 +393,10 @@ __global__ void __launch_bounds__(kMaxThreads, (kPlane <= 2048 ? 2 : 1)) psf_cha
   carve<kPlane>(sm, smem_raw, p, kTps, 0);
   init_barriers(p, sm);
 
-  Producer pr;
-  if (g.warp == 0) {
-    producer_init(pr, p, g);
-    if (!(p.dbg & 8)) producer_pump<false, kTps>(pr, p, g, sm, false);
+  if (threadIdx.x == 0 && !(p.dbg & 8)) {  // prime the ring
+    for (int s = 0; s < p.stages; ++s) issue_stage_index<false, kTps>(s, s, p, g, sm);
   }
+  int gs = 0;  // stages consumed so far (identical in every warp)
 
   const int S = p.stages;
   const int nthr_c = g.ncw * 32;
@@ -492,10 +451,7 @@ __global__ void __launch_bounds__(kMaxThreads, (kPlane <= 2048 ? 2 : 1)) psf_cha
 
         const float* vown = Vs + (j - g.blk_start);
         for (int tg = 0; tg < g.ngroups; ++tg) {
-          if (!(p.dbg & 8)) {
-            if (g.warp == 0 && pr.ahead == 0) producer_pump<false, kTps>(pr, p, g, sm, true);
-            mbar_wait(sm.full_u32 + slot * 8, parity);
-          }
+          if (!(p.dbg & 8)) mbar_wait(sm.full_u32 + slot * 8, parity);
           const float* wst = sm.ring + slot * sm.stage_f + g.warp * kTile + 4 * g.lane;
           // The deferred cluster wait must be executed by whole warps: decide it from warp-uniform values
           // (tile origin, tap offset) - does any row of this tile reach past the block with this tap?
@@ -574,14 +530,11 @@ __global__ void __launch_bounds__(kMaxThreads, (kPlane <= 2048 ? 2 : 1)) psf_cha
           }
           __syncwarp();
           if (!(p.dbg & 8)) {
-            if (g.lane == 0) mbar_arrive(sm.empty_u32 + slot * 8);  // this warp is done with the stage
+            if (g.lane == 0) release_stage<false, kTps>(gs, slot, p, g, sm);  // this warp is done with the stage
+            ++gs;
             if (++slot == S) {
               slot = 0;
               parity ^= 1u;
-            }
-            if (g.warp == 0) {
-              --pr.ahead;
-              producer_pump<false, kTps>(pr, p, g, sm, false);
             }
           }
         }
@@ -636,11 +589,10 @@ __global__ void __launch_bounds__(kMaxThreads, (kPlane <= 2048 ? 2 : 1)) psf_cha
   carve<kPlane>(sm, smem_raw, p, kTps, kPadB);
   init_barriers(p, sm);
 
-  Producer pr;
-  if (g.warp == 0) {
-    producer_init(pr, p, g);
-    producer_pump<true, kTps>(pr, p, g, sm, false);
+  if (threadIdx.x == 0) {  // prime the ring
+    for (int s = 0; s < p.stages; ++s) issue_stage_index<true, kTps>(s, s, p, g, sm);
   }
+  int gs = 0;  // stages consumed so far (identical in every warp)
 
   const int S = p.stages;
   const int nthr_c = g.ncw * 32;
@@ -704,7 +656,6 @@ __global__ void __launch_bounds__(kMaxThreads, (kPlane <= 2048 ? 2 : 1)) psf_cha
         }
         const float* gown = Gs + (j - g.blk_start);
         for (int tg = 0; tg < g.ngroups; ++tg) {
-          if (g.warp == 0 && pr.ahead == 0) producer_pump<true, kTps>(pr, p, g, sm, true);
           mbar_wait(sm.full_u32 + slot * 8, parity);
           const float* wst = sm.ring + slot * sm.stage_f + g.warp * kTile + 4 * g.lane;
           {
@@ -774,14 +725,11 @@ __global__ void __launch_bounds__(kMaxThreads, (kPlane <= 2048 ? 2 : 1)) psf_cha
             }
           }
           __syncwarp();
-          if (g.lane == 0) mbar_arrive(sm.empty_u32 + slot * 8);
+          if (g.lane == 0) release_stage<true, kTps>(gs, slot, p, g, sm);
+          ++gs;
           if (++slot == S) {
             slot = 0;
             parity ^= 1u;
-          }
-          if (g.warp == 0) {
-            --pr.ahead;
-            producer_pump<true, kTps>(pr, p, g, sm, false);
           }
         }
         if (cw_pending) {
