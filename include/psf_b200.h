@@ -47,16 +47,26 @@ typedef enum { PSF_F32 = 0, PSF_F64 = 1 } psf_dtype;
 
 /* Which chain implementation ran / should run. */
 typedef enum {
-  PSF_PATH_AUTO = 0,    /* fused resident kernel when the shape allows, else per-factor  */
-  PSF_PATH_GENERIC = 1, /* one launch per factor, V through L2/HBM (any shape, f32/f64)  */
-  PSF_PATH_FUSED = 2    /* cluster kernel, V block resident in SMEM across all factors   */
+  PSF_PATH_AUTO = 0,     /* fused resident kernel when the shape allows, else per-factor  */
+  PSF_PATH_GENERIC = 1,  /* one launch per factor, V through L2/HBM (any shape, f32/f64)  */
+  PSF_PATH_FUSED = 2,    /* cluster kernel, V block resident in SMEM across all factors   */
+  PSF_PATH_FUSED_GEN1 = 3 /* request only: the first-generation cluster kernel (contiguous row
+                            blocks); reported back as PSF_PATH_FUSED                      */
 } psf_path;
 
 /* Element strides of a stack of factors W[factor][sample][row][tap].
  * Reference layout  ("row-major", W_m = fs[m](data) of shape [B,n,L], one tensor per m
  * stacked to [n_W,B,n,L]):      factor=B*n*L sample=n*L row=L tap=1
  * Streaming layout  ("tap-major", what the fused kernel wants, [n_W,L,B,n]):
- *                               factor=L*B*n sample=n   row=1 tap=B*n                */
+ *                               factor=L*B*n sample=n   row=1 tap=B*n
+ *
+ * Row order.  psf_chain_desc.interleave = Q > 1 says that the ROW axis of W and dW (not of V) is
+ * stored "quad-interleaved": logical row i, quad u = i>>2, sits at position
+ *     p(i) = (u mod Q) * (n/Q) + 4 * (u div Q) + (i & 3)
+ * i.e. the row quads are dealt round-robin to Q blocks of n/Q rows.  The second-generation fused
+ * kernel runs a Q-CTA cluster per sample in which CTA q owns block q; ask
+ * psf_chain_preferred_interleave() for the Q a problem wants (1 = natural order) and produce W in
+ * that order (row-wise generators only need their input rows permuted once).            */
 typedef struct {
   int64_t factor, sample, row, tap;
 } psf_wstrides;
@@ -97,6 +107,8 @@ typedef struct {
   psf_wstrides ws;            /* strides of W (and of dW)            */
   const int64_t* offsets;     /* HOST array [L]; NULL = chord offsets 0,1,2,4,... mod n */
   psf_path path;              /* PSF_PATH_AUTO normally              */
+  int interleave;             /* row order of W/dW: 0 or 1 natural, Q > 1 quad-interleaved (above);
+                                 Q > 1 is accepted only when it equals psf_chain_preferred_interleave() */
 } psf_chain_desc;
 
 /* Bytes of device workspace psf_chain_fwd / psf_chain_bwd need for this problem.
@@ -119,6 +131,19 @@ int psf_chain_bwd(const psf_chain_desc* d, const void* W, const void* dOut, void
  * streaming layout. */
 int psf_w_relayout(psf_dtype dtype, const void* src, psf_wstrides ss, void* dst, psf_wstrides ds,
                    int n_W, int64_t B, int64_t n, int L, psf_stream_t stream);
+
+/* Same with a row order per side (1 = natural, Q > 1 = quad-interleaved; needs n % (4Q) == 0). */
+int psf_w_relayout_ex(psf_dtype dtype, const void* src, psf_wstrides ss, int src_interleave, void* dst,
+                      psf_wstrides ds, int dst_interleave, int n_W, int64_t B, int64_t n, int L,
+                      psf_stream_t stream);
+
+/* Row interleave Q the fastest fused kernel wants for this problem (desc.interleave and desc.ws are
+ * ignored): Q > 1 for f32, C = 8, n = 2^p in [4096, 16384], L = p+1 chord offsets; otherwise 1. */
+int psf_chain_preferred_interleave(const psf_chain_desc* d);
+
+/* Which fused kernel generation psf_chain_fwd would launch for this descriptor: 2 (quad-interleaved
+ * clusters), 1 (contiguous row blocks) or 0 (per-factor path). */
+int psf_chain_fused_generation(const psf_chain_desc* d);
 
 /* Launch geometry the fused path would use for this problem (for benches / docs):
  * cluster size, rows per CTA, threads per CTA, dynamic SMEM bytes, resident clusters.

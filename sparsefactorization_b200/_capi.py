@@ -10,7 +10,7 @@ from . import build as _build
 
 PSF_OK = 0
 PSF_F32, PSF_F64 = 0, 1
-PATH_AUTO, PATH_GENERIC, PATH_FUSED = 0, 1, 2
+PATH_AUTO, PATH_GENERIC, PATH_FUSED, PATH_FUSED_GEN1 = 0, 1, 2, 3
 MAX_TAPS = 32
 
 
@@ -25,6 +25,7 @@ class ChainDesc(C.Structure):
         ("ws", WStrides),
         ("offsets", C.POINTER(C.c_int64)),
         ("path", C.c_int),
+        ("interleave", C.c_int),
     ]
 
 
@@ -49,6 +50,10 @@ _SIGNATURES = {
                                 C.c_size_t, C.POINTER(C.c_int), C.c_void_p]),
     "psf_w_relayout": (C.c_int, [C.c_int, C.c_void_p, WStrides, C.c_void_p, WStrides, C.c_int, C.c_int64, C.c_int64,
                                  C.c_int, C.c_void_p]),
+    "psf_w_relayout_ex": (C.c_int, [C.c_int, C.c_void_p, WStrides, C.c_int, C.c_void_p, WStrides, C.c_int, C.c_int,
+                                    C.c_int64, C.c_int64, C.c_int, C.c_void_p]),
+    "psf_chain_preferred_interleave": (C.c_int, [C.POINTER(ChainDesc)]),
+    "psf_chain_fused_generation": (C.c_int, [C.POINTER(ChainDesc)]),
     "psf_chain_fused_plan": (C.c_int, [C.POINTER(ChainDesc), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                        C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
 }

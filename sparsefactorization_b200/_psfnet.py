@@ -12,7 +12,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import _capi
-from .chain import chord_chain
+from .chain import chord_chain, preferred_interleave, row_permutation
 
 
 # ---------------------------------------------------------------------------------------------
@@ -147,8 +147,12 @@ class _TapMajorLastLinear(torch.autograd.Function):
         return dh, dw, db
 
 
-def generate_factors(fs: Sequence[MLPBlock], data: torch.Tensor) -> torch.Tensor:
+def generate_factors(fs: Sequence[MLPBlock], data: torch.Tensor, interleave: int = 1) -> torch.Tensor:
     """``W[m] = fs[m](data)`` for every m (psf.py:175), computed as batched GEMMs.
+
+    ``interleave = Q > 1``: the generators are row-wise, so permuting the rows of ``data`` once makes
+    every W (and dW on the way back) come out in the quad-interleaved row order the second-generation
+    chain kernel streams (include/psf_b200.h); the permutation's backward is autograd's.
 
     data ``[B, n, E]`` -> logical ``[n_W, B, n, L]`` stored tap-major (physical ``[n_W, L, B*n]``):
     the last Linear of every generator is evaluated as ``weight @ hidden^T`` so its output lands
@@ -157,6 +161,8 @@ def generate_factors(fs: Sequence[MLPBlock], data: torch.Tensor) -> torch.Tensor
     """
     n_W = len(fs)
     B, n, E = data.shape
+    if interleave > 1:
+        data = data.view(B, n // (4 * interleave), interleave, 4, E).permute(0, 2, 1, 3, 4).reshape(B, n, E)
     x_shared = data.reshape(B * n, E)
     if not _same_structure(fs):
         # heterogeneous generators: evaluate one by one (reference order), then re-lay
@@ -197,8 +203,12 @@ class PSFChainMixin:
     """forward() tail shared by the variants: W generation + fused chain (psf.py:165-188)."""
 
     def _apply_chain(self, data: torch.Tensor, V: torch.Tensor) -> torch.Tensor:
-        W = generate_factors(self.fs, data)
-        return chord_chain(W, V, use_residuals=self.use_residuals)
+        n_W, (B, n, _) = len(self.fs), data.shape
+        L = self.fs[0].network[-1].out_features
+        # (heterogeneous generators are evaluated one by one in the reference layout: natural row order)
+        Q = preferred_interleave(n_W, B, n, L, V.shape[2]) if V.dtype == torch.float32 and _same_structure(self.fs) else 1
+        W = generate_factors(self.fs, data, Q)
+        return chord_chain(W, V, use_residuals=self.use_residuals, interleave=Q)
 
     def _make_indices(self):
         self.chord_indicies = chord_index_tensor(self.n_vec, self.n_links, "cuda" if self.use_cuda else "cpu")

@@ -13,8 +13,9 @@ import torch
 
 from . import _capi
 
-_PATHS = {"auto": _capi.PATH_AUTO, "generic": _capi.PATH_GENERIC, "fused": _capi.PATH_FUSED}
-_PATH_NAMES = {v: k for k, v in _PATHS.items()}
+_PATHS = {"auto": _capi.PATH_AUTO, "generic": _capi.PATH_GENERIC, "fused": _capi.PATH_FUSED,
+          "fused_gen1": _capi.PATH_FUSED_GEN1}
+_PATH_NAMES = {_capi.PATH_AUTO: "auto", _capi.PATH_GENERIC: "generic", _capi.PATH_FUSED: "fused"}
 _DTYPES = {torch.float32: _capi.PSF_F32, torch.float64: _capi.PSF_F64}
 
 last_path_used: Optional[str] = None   # "fused" / "generic": which implementation the last forward took
@@ -91,7 +92,8 @@ def _dense_nonoverlapping(t: torch.Tensor) -> bool:
     return True
 
 
-def _desc(W: torch.Tensor, V0: torch.Tensor, residual: bool, offs_arr, path: int) -> _capi.ChainDesc:
+def _desc(W: torch.Tensor, V0: torch.Tensor, residual: bool, offs_arr, path: int,
+          interleave: int = 1) -> _capi.ChainDesc:
     n_W, B, n, L = W.shape
     d = _capi.ChainDesc()
     d.B, d.n, d.C = B, n, V0.shape[2]
@@ -102,12 +104,13 @@ def _desc(W: torch.Tensor, V0: torch.Tensor, residual: bool, offs_arr, path: int
     d.ws = _capi.WStrides(sf, sb, sr, st)
     d.offsets = C.cast(offs_arr, C.POINTER(C.c_int64)) if offs_arr is not None else None
     d.path = path
+    d.interleave = int(interleave)
     return d
 
 
 class _ChordChainFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, W, V0, residual, offsets, path):
+    def forward(ctx, W, V0, residual, offsets, path, interleave=1):
         global last_path_used
         lib = _capi.load()
         _require_cuda(W, V0)
@@ -125,7 +128,7 @@ class _ChordChainFn(torch.autograd.Function):
         need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         out = torch.empty_like(V0)
         with torch.cuda.device(W.device):
-            d = _desc(W, V0, residual, offs_arr, _PATHS[path])
+            d = _desc(W, V0, residual, offs_arr, _PATHS[path], interleave)
             nbytes = lib.psf_chain_workspace_bytes(C.byref(d), 1 if need_grad else 0)
             ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=W.device)
             used = C.c_int(0)
@@ -140,7 +143,8 @@ class _ChordChainFn(torch.autograd.Function):
             ctx.ws = ws
             ctx.residual = residual
             ctx.offs_list = offs_list
-            ctx.path_used = used.value
+            ctx.path_used = _PATHS[path] if path == "fused_gen1" else used.value
+            ctx.interleave = interleave
             ctx.v_shape = V0.shape
         return out
 
@@ -156,18 +160,19 @@ class _ChordChainFn(torch.autograd.Function):
         dV0 = torch.empty(ctx.v_shape, dtype=W.dtype, device=W.device)
         with torch.cuda.device(W.device):
             V_like = dV0
-            d = _desc(W, V_like, ctx.residual, offs_arr, ctx.path_used)   # same path as the forward: state layout
+            # same path as the forward (the saved states are laid out per path)
+            d = _desc(W, V_like, ctx.residual, offs_arr, ctx.path_used, ctx.interleave)
             used = C.c_int(0)
             stream = torch.cuda.current_stream().cuda_stream
             with _Timed("bwd"):
                 rc = lib.psf_chain_bwd(C.byref(d), W.data_ptr(), dOut.data_ptr(), dW.data_ptr(), dV0.data_ptr(),
                                        ctx.ws.data_ptr(), ctx.ws.numel(), C.byref(used), stream)
             _capi.check(rc, "psf_chain_bwd")
-        return dW, dV0, None, None, None
+        return dW, dV0, None, None, None, None
 
 
 def chord_chain(W: torch.Tensor, V0: torch.Tensor, use_residuals: bool = False,
-                offsets: Optional[Sequence[int]] = None, path: str = "auto") -> torch.Tensor:
+                offsets: Optional[Sequence[int]] = None, path: str = "auto", interleave: int = 1) -> torch.Tensor:
     """Apply ``W[n_W-1] ... W[0]`` to ``V0``.
 
     W  : logical shape ``[n_W, B, n, L]``, any dense stride order.  The streaming ("tap-major")
@@ -175,9 +180,12 @@ def chord_chain(W: torch.Tensor, V0: torch.Tensor, use_residuals: bool = False,
          kernel consumes directly; the reference order (physical ``[n_W, B, n, L]``) runs through
          the per-factor path.
     V0 : ``[B, n, C]``.   offsets: tap offsets (default chord: 0, 1, 2, 4, ... mod n).
+    interleave : ``Q > 1`` says the row axis of W (and of the returned dW) is stored quad-interleaved
+         (include/psf_b200.h; :func:`preferred_interleave` / :func:`row_permutation`), which is what the
+         second-generation fused kernel streams.  V0 and the result stay in natural row order.
     Returns ``V_{n_W}`` with ``V_m = W_m V_{m-1} (+ V_0 if use_residuals)``.
     """
-    return _ChordChainFn.apply(W, V0, bool(use_residuals), offsets, path)
+    return _ChordChainFn.apply(W, V0, bool(use_residuals), offsets, path, int(interleave))
 
 
 def empty_tap_major(n_W: int, B: int, n: int, L: int, dtype=torch.float32, device="cuda") -> torch.Tensor:
@@ -185,18 +193,54 @@ def empty_tap_major(n_W: int, B: int, n: int, L: int, dtype=torch.float32, devic
     return torch.empty(n_W, L, B, n, dtype=dtype, device=device).permute(0, 2, 3, 1)
 
 
-def to_tap_major(W: torch.Tensor) -> torch.Tensor:
+def to_tap_major(W: torch.Tensor, interleave: int = 1, src_interleave: int = 1) -> torch.Tensor:
     """Re-lay a logical ``[n_W, B, n, L]`` stack into the streaming order with the library's
-    tiled transpose (values unchanged).  Not differentiable; for benches and tests."""
+    tiled transpose (values unchanged), optionally changing the row order (``interleave`` of the
+    result, ``src_interleave`` of the input).  Not differentiable; for benches and tests."""
     lib = _capi.load()
     _require_cuda(W)
     n_W, B, n, L = W.shape
     dst = empty_tap_major(n_W, B, n, L, W.dtype, W.device)
     with torch.cuda.device(W.device):
-        rc = lib.psf_w_relayout(_DTYPES[W.dtype], W.data_ptr(), _capi.WStrides(*W.stride()), dst.data_ptr(),
-                                _capi.WStrides(*dst.stride()), n_W, B, n, L, torch.cuda.current_stream().cuda_stream)
-        _capi.check(rc, "psf_w_relayout")
+        rc = lib.psf_w_relayout_ex(_DTYPES[W.dtype], W.data_ptr(), _capi.WStrides(*W.stride()), int(src_interleave),
+                                   dst.data_ptr(), _capi.WStrides(*dst.stride()), int(interleave), n_W, B, n, L,
+                                   torch.cuda.current_stream().cuda_stream)
+        _capi.check(rc, "psf_w_relayout_ex")
     return dst
+
+
+def row_permutation(n: int, interleave: int, device="cpu") -> torch.Tensor:
+    """``perm`` with ``x_interleaved = x_natural[perm]``: the natural row stored at every position of a
+    quad-interleaved row axis (include/psf_b200.h: position ``(u % Q)*(n/Q) + 4*(u//Q) + (i & 3)``, ``u = i >> 2``)."""
+    Q = int(interleave)
+    idx = torch.arange(n, device=device)
+    if Q <= 1:
+        return idx
+    if n % (4 * Q):
+        raise ValueError("quad interleave needs n % (4*Q) == 0")
+    return idx.view(n // (4 * Q), Q, 4).permute(1, 0, 2).reshape(n)
+
+
+def _shape_desc(n_W: int, B: int, n: int, L: int, C_: int, residual: bool, interleave: int, path: str):
+    d = _capi.ChainDesc()
+    d.B, d.n, d.C, d.n_W, d.L, d.residual, d.dtype = B, n, C_, n_W, L, int(residual), _capi.PSF_F32
+    d.ws = _capi.WStrides(L * B * n, n, 1, B * n)
+    d.offsets = None
+    d.path = _PATHS[path]
+    d.interleave = int(interleave)
+    return d
+
+
+def preferred_interleave(n_W: int, B: int, n: int, L: int, C_: int = 8) -> int:
+    """Row interleave Q the fastest fused kernel wants for this problem (1 = natural order)."""
+    lib = _capi.load()
+    return int(lib.psf_chain_preferred_interleave(C.byref(_shape_desc(n_W, B, n, L, C_, True, 1, "auto"))))
+
+
+def fused_generation(n_W: int, B: int, n: int, L: int, C_: int = 8, interleave: int = 1, path: str = "auto") -> int:
+    """2 / 1 / 0: which fused kernel generation a tap-major problem with this row order would run."""
+    lib = _capi.load()
+    return int(lib.psf_chain_fused_generation(C.byref(_shape_desc(n_W, B, n, L, C_, True, interleave, path))))
 
 
 def chord_chain_list(Ws: Sequence[torch.Tensor], V0: torch.Tensor, use_residuals: bool = False,
@@ -205,14 +249,11 @@ def chord_chain_list(Ws: Sequence[torch.Tensor], V0: torch.Tensor, use_residuals
     return chord_chain(torch.stack(list(Ws), 0), V0, use_residuals, offsets, path)
 
 
-def fused_plan(n_W: int, B: int, n: int, L: int, C_: int = 8, residual: bool = True):
+def fused_plan(n_W: int, B: int, n: int, L: int, C_: int = 8, residual: bool = True, interleave: int = 1,
+               path: str = "auto"):
     """Launch geometry of the fused path for a tap-major problem, or None if unsupported."""
     lib = _capi.load()
-    d = _capi.ChainDesc()
-    d.B, d.n, d.C, d.n_W, d.L, d.residual, d.dtype = B, n, C_, n_W, L, int(residual), _capi.PSF_F32
-    d.ws = _capi.WStrides(L * B * n, n, 1, B * n)
-    d.offsets = None
-    d.path = _capi.PATH_AUTO
+    d = _shape_desc(n_W, B, n, L, C_, residual, interleave, path)
     vals = [C.c_int(0) for _ in range(5)]
     rc = lib.psf_chain_fused_plan(C.byref(d), *[C.byref(v) for v in vals])
     if rc != 0:

@@ -31,17 +31,33 @@ int make_args(const psf_chain_desc* d, PsfChainArgs* a) {
   a->L = d->L;
   a->residual = d->residual ? 1 : 0;
   a->ws = d->ws;
+  a->interleave = d->interleave < 1 ? 1 : d->interleave;
   return normalise_offsets(d->offsets, d->n, d->L, &a->offs);
 }
 
-bool use_fused(const psf_chain_desc* d, const PsfChainArgs& a, const void* W, const void* p1, const void* p2,
-               const void* ws, int* status) {
+// Which fused generation serves this call: 2, 1, or 0 = per-factor path (then *status says whether that is
+// acceptable).  An interleaved row order exists only for generation 2.
+int use_fused(const psf_chain_desc* d, const PsfChainArgs& a, const void* W, const void* p1, const void* p2,
+              const void* ws, int* status) {
   *status = PSF_OK;
-  if (d->path == PSF_PATH_GENERIC) return false;
   PsfFusedPlan plan;
-  const bool ok = d->dtype == PSF_F32 && psf_fused_plan(a, &plan) == PSF_OK && psf_fused_buffers_ok(a, W, p1, p2, ws);
-  if (!ok && d->path == PSF_PATH_FUSED) *status = PSF_ERR_UNSUPPORTED;
-  return ok;
+  const bool f32 = d->dtype == PSF_F32;
+  if (a.interleave > 1) {
+    if (d->path != PSF_PATH_GENERIC && d->path != PSF_PATH_FUSED_GEN1 && f32 && psf_chain2_plan(a, &plan) == PSF_OK &&
+        psf_fused_buffers_ok(a, W, p1, p2, ws))
+      return 2;
+    *status = PSF_ERR_UNSUPPORTED;
+    return 0;
+  }
+  if (d->path == PSF_PATH_GENERIC) return 0;
+  if (!f32 || !psf_fused_buffers_ok(a, W, p1, p2, ws)) {
+    if (d->path != PSF_PATH_AUTO) *status = PSF_ERR_UNSUPPORTED;
+    return 0;
+  }
+  if (d->path != PSF_PATH_FUSED_GEN1 && psf_chain2_plan(a, &plan) == PSF_OK) return 2;
+  if (psf_fused_plan(a, &plan) == PSF_OK) return 1;
+  if (d->path != PSF_PATH_AUTO) *status = PSF_ERR_UNSUPPORTED;
+  return 0;
 }
 
 }  // namespace
@@ -181,8 +197,11 @@ int psf_chain_fwd(const psf_chain_desc* d, const void* W, const void* V0, void* 
   if (workspace == nullptr || workspace_bytes < psf_chain_workspace_bytes(d, save_states)) return PSF_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   int status;
-  if (use_fused(d, a, W, V0, out, workspace, &status)) {
+  const int gen = use_fused(d, a, W, V0, out, workspace, &status);
+  if (gen) {
     if (path_used) *path_used = PSF_PATH_FUSED;
+    if (gen == 2)
+      return psf_chain2_fwd(a, (const float*)W, (const float*)V0, (float*)out, (float*)workspace, save_states, st);
     return psf_fused_chain_fwd(a, (const float*)W, (const float*)V0, (float*)out, (float*)workspace, save_states, st);
   }
   if (status) return status;
@@ -205,13 +224,15 @@ int psf_chain_bwd(const psf_chain_desc* d, const void* W, const void* dOut, void
   cudaStream_t st = (cudaStream_t)stream;
   int status;
   // the saved states are laid out per path, so the backward pass must take the path the forward took
-  bool fused = use_fused(d, a, W, dOut, dV0, workspace, &status);
-  if (fused && (reinterpret_cast<uintptr_t>(dW) & 15) != 0) {
-    fused = false;
-    if (d->path == PSF_PATH_FUSED) status = PSF_ERR_UNSUPPORTED;
+  int gen = use_fused(d, a, W, dOut, dV0, workspace, &status);
+  if (gen && (reinterpret_cast<uintptr_t>(dW) & 15) != 0) {
+    gen = 0;
+    if (d->path != PSF_PATH_AUTO || a.interleave > 1) status = PSF_ERR_UNSUPPORTED;
   }
-  if (fused) {
+  if (gen) {
     if (path_used) *path_used = PSF_PATH_FUSED;
+    if (gen == 2)
+      return psf_chain2_bwd(a, (const float*)W, (const float*)dOut, (float*)dW, (float*)dV0, (float*)workspace, st);
     return psf_fused_chain_bwd(a, (const float*)W, (const float*)dOut, (float*)dW, (float*)dV0, (float*)workspace, st);
   }
   if (status) return status;
@@ -226,7 +247,31 @@ int psf_chain_bwd(const psf_chain_desc* d, const void* W, const void* dOut, void
 int psf_w_relayout(psf_dtype dtype, const void* src, psf_wstrides ss, void* dst, psf_wstrides ds, int n_W, int64_t B,
                    int64_t n, int L, psf_stream_t stream) {
   if (src == nullptr || dst == nullptr || n_W < 0 || B < 0 || n < 0 || L < 1 || L > PSF_MAX_TAPS) return PSF_ERR_ARG;
-  return psf_generic_relayout(dtype, src, ss, dst, ds, n_W, B, n, L, (cudaStream_t)stream);
+  return psf_generic_relayout(dtype, src, ss, 1, dst, ds, 1, n_W, B, n, L, (cudaStream_t)stream);
+}
+
+int psf_w_relayout_ex(psf_dtype dtype, const void* src, psf_wstrides ss, int src_interleave, void* dst, psf_wstrides ds,
+                      int dst_interleave, int n_W, int64_t B, int64_t n, int L, psf_stream_t stream) {
+  if (src == nullptr || dst == nullptr || n_W < 0 || B < 0 || n < 0 || L < 1 || L > PSF_MAX_TAPS) return PSF_ERR_ARG;
+  const int qs = src_interleave < 1 ? 1 : src_interleave, qd = dst_interleave < 1 ? 1 : dst_interleave;
+  if ((qs > 1 && n % (4 * (int64_t)qs)) || (qd > 1 && n % (4 * (int64_t)qd))) return PSF_ERR_ARG;
+  return psf_generic_relayout(dtype, src, ss, qs, dst, ds, qd, n_W, B, n, L, (cudaStream_t)stream);
+}
+
+int psf_chain_preferred_interleave(const psf_chain_desc* d) {
+  PsfChainArgs a;
+  if (make_args(d, &a) != PSF_OK || d->dtype != PSF_F32) return 1;
+  const int Q = psf_chain2_interleave_for(a);
+  return Q > 1 ? Q : 1;
+}
+
+int psf_chain_fused_generation(const psf_chain_desc* d) {
+  PsfChainArgs a;
+  if (make_args(d, &a) != PSF_OK || d->dtype != PSF_F32 || d->path == PSF_PATH_GENERIC) return 0;
+  PsfFusedPlan plan;
+  if (d->path != PSF_PATH_FUSED_GEN1 && psf_chain2_plan(a, &plan) == PSF_OK) return 2;
+  if (a.interleave > 1) return 0;
+  return psf_fused_plan(a, &plan) == PSF_OK ? 1 : 0;
 }
 
 int psf_chain_fused_plan(const psf_chain_desc* d, int* cluster, int* rows_per_cta, int* threads, int* smem_bytes,
@@ -236,8 +281,11 @@ int psf_chain_fused_plan(const psf_chain_desc* d, int* cluster, int* rows_per_ct
   if (rc) return rc;
   if (d->dtype != PSF_F32) return PSF_ERR_UNSUPPORTED;
   PsfFusedPlan plan;
-  rc = psf_fused_plan(a, &plan);
-  if (rc) return rc;
+  if (d->path == PSF_PATH_FUSED_GEN1 || psf_chain2_plan(a, &plan) != PSF_OK) {
+    if (a.interleave > 1) return PSF_ERR_UNSUPPORTED;
+    rc = psf_fused_plan(a, &plan);
+    if (rc) return rc;
+  }
   if (cluster) *cluster = plan.cluster;
   if (rows_per_cta) *rows_per_cta = plan.rows_per_cta;
   if (threads) *threads = plan.threads;

@@ -1,0 +1,826 @@
+// Fused chord-factor chain, second generation ("quad-interleaved clusters"), sm_100a, fp32, C = 8,
+// n = 2^p rows with the standard chord offsets 0,1,2,4,...,n/2 (L = p+1 taps).
+//
+// One cluster of Q = n/J CTAs owns one sample (J = 2048 rows per CTA).  Unlike the first generation
+// (psf_chain_sm100.cu: contiguous row blocks), CTA q owns the row QUADS u = i>>2 with u mod Q == q:
+//
+//     row i = 4*(lq*Q + q) + lo,   lq = local quad index, lo = 0..3
+//
+// With the CTA bits at the BOTTOM of the quad index, a chord offset either
+//   * stays inside the thread's quad pair     (offsets 1, 2: register shuffles of two quads),
+//   * moves to a sibling CTA, same local quad (offsets 4..2Q: "remote" taps, log2 Q of them), or
+//   * moves inside the CTA by a power of two  (offsets >= 4Q: local quad lq + 2^t, cyclic in J),
+// so there is no halo, the cyclic wrap is an AND on a shared-memory address, every operand access is
+// an aligned 128-bit quad, and the whole tap schedule is known at compile time: the inner loop is
+// straight-line code (no per-tap locality / alignment branches).  Remote operands are exactly
+// log2(Q)/(log2(n)+1) of the reads (3/15 at n = 16384) and are fetched with coalesced ld.global.cg
+// from the sibling's published state (L2 resident), staged in registers behind local taps.
+//
+// W / dW stream: physical layout [n_W][L][B][n'] where n' is the row axis in "quad-interleaved"
+// order p(i) = q*J + 4*lq + lo (desc.interleave = Q): each CTA's rows of one tap are one contiguous
+// 8 KB run.  W goes global -> registers directly (coalesced 512 B per warp and tap, read exactly
+// once, prefetched into L2 one pass ahead and into registers a few taps ahead); it does not pass
+// through shared memory, which carries only the V/G operand traffic (the co-critical resource).
+//
+// State handling is the first generation's: the CTA's block of the current state sits in shared
+// memory (channel-major, read-only during a factor), every new state goes to global memory
+// (forward: these are the saved states of the backward pass) and is pulled back with TMA bulk
+// copies at the factor boundary; one hardware cluster barrier per factor orders the exchange.
+//
+// Reference semantics: SyntheticExperiments/psf.py:167-188 (loop + residual), spmul_cuda.cu:24,
+// :79-80, :105-108 (per-factor formulas).
+#include <cstdlib>
+
+#include "psf_internal.cuh"
+#include "psf_ptx.cuh"
+
+namespace {
+
+// warps per CTA: the forward pass fits 128 registers (8 warps, 2 CTAs per SM); the backward pass keeps two
+// 32-register operand sets (accumulators and the stationary V_{m-1} rows) and runs 6 warps at 168 registers
+#ifndef PSF2_NW_FWD
+#define PSF2_NW_FWD 8
+#endif
+#ifndef PSF2_NW_BWD
+#define PSF2_NW_BWD 6
+#endif
+constexpr int kNWF = PSF2_NW_FWD;
+constexpr int kNWB = PSF2_NW_BWD;
+constexpr int kTileRows = 128;       // rows per warp tile (32 lanes x one quad)
+
+struct Chain2Params {
+  const float* W;
+  float* dW;
+  const float* Vin;   // fwd: V0 [B,n,8];   bwd: dOut [B,n,8]  (natural layout)
+  float* Vout;        // fwd: out [B,n,8];  bwd: dV0 [B,n,8]
+  float* states;      // [slot][B][Q][8][J]
+  float* gx;          // bwd exchange, per cluster [2][ncl][Q][8][J]
+  float* racc;        // bwd residual accumulator, per cluster [ncl][Q][8][J]
+  long long sWf, sWb, sWt;  // factor / sample / tap strides of W and dW (elements); row stride 1
+  int B, n_W, residual, save_states;
+  int dbg;
+};
+
+template <int V>
+struct IC {
+  static constexpr int value = V;
+  constexpr operator int() const { return V; }
+};
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(IC<I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+
+// Compile-time geometry and tap schedule.
+//   taps: k = 0 (offset 0), 1, 2 (offsets 1, 2), 3+r (remote r, quad offset 2^r), 3+NREM+t (local t,
+//   element offset 4<<t inside the CTA's J rows).
+//   R-quads: the NR = max(NREM,1) quads that are staged in registers: remote taps, or - without a cluster -
+//   the local quad of tap 3, which the offset-1/2 taps need next to the thread's own quad.
+//   Schedule of one pass: plain local taps are split into NR+1 groups; R(0) is issued after group 0,
+//   consumed after group 1 together with taps 0,1,2 ("head"), R(r) is issued when R(r-1) has been consumed.
+//   W registers are loaded in consumption order: idx -> tap k = k_at(idx).  The backward pass loads the
+//   W values of taps 1,2 separately (they straddle two quads), so its sequence skips them.
+template <int LOGJ, int LOGQ, bool BWD>
+struct Geo {
+  static constexpr int NW = BWD ? kNWB : kNWF;
+  static constexpr int NT = (1 << LOGJ) / kTileRows;  // warp tiles per CTA block
+  static constexpr int J = 1 << LOGJ;
+  static constexpr int Q = 1 << LOGQ;
+  static constexpr int NQ = J / 4;  // local quads
+  static constexpr int NLOC = LOGJ - 2;
+  static constexpr int NREM = LOGQ;
+  static constexpr int L = 3 + NREM + NLOC;
+  static constexpr int NPASS = (NT + NW - 1) / NW;
+  static constexpr int NR = NREM > 0 ? NREM : 1;
+  static constexpr int SKIP0 = NREM > 0 ? 0 : 1;  // local tap 0 is R(0) when there is no cluster
+  static constexpr int P = NLOC - SKIP0;          // plain local taps
+  static constexpr int NGRP = NR + 1;
+  static constexpr int HEADN = BWD ? 2 : 4;
+  static constexpr int SEQ = P + HEADN + (NR - 1);
+  __host__ __device__ static constexpr int plo(int g) { return g * P / NGRP; }
+  __host__ __device__ static constexpr int kloc(int p) { return 3 + NREM + p + SKIP0; }
+  __host__ __device__ static constexpr int headk(int h) { return BWD ? (h == 0 ? 3 : 0) : h; }
+  __host__ __device__ static constexpr int k_at(int idx) {
+    int s = 0;
+    for (int g = 0; g < NGRP; ++g) {
+      for (int pp = plo(g); pp < plo(g + 1); ++pp) {
+        if (s == idx) return kloc(pp);
+        ++s;
+      }
+      if (g == 1) {
+        for (int h = 0; h < HEADN; ++h) {
+          if (s == idx) return headk(h);
+          ++s;
+        }
+      } else if (g >= 2) {
+        if (s == idx) return 3 + (g - 1);
+        ++s;
+      }
+    }
+    return -1;
+  }
+  __host__ __device__ static constexpr int idx_of(int k) {
+    for (int i = 0; i < SEQ; ++i)
+      if (k_at(i) == k) return i;
+    return -1;
+  }
+};
+
+__device__ __forceinline__ float4 ldg_w4(const float* p) {  // W: read once, keep out of L1
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float2 ldg_w2(const float* p) {
+  float2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ldg_w1(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+// exchanged state written by sibling CTAs during this kernel: L2-coherent load, pinned in program order
+__device__ __forceinline__ float4 ldcg4_v(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+__device__ __forceinline__ void st_cs2(float* p, float a, float b) { __stcs(reinterpret_cast<float2*>(p), make_float2(a, b)); }
+
+// this CTA's block of a published state -> shared memory (8 channel planes of J floats, contiguous)
+template <int J>
+__device__ __forceinline__ void refresh_block(uint32_t state_u32, uint32_t vbar, const float* blk) {
+  mbar_expect_tx(vbar, (uint32_t)(CT * J * 4));
+#pragma unroll
+  for (int ch = 0; ch < CT; ++ch) tma_load_1d(state_u32 + (uint32_t)(ch * J) * 4u, blk + ch * J, (uint32_t)J * 4u, vbar);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward
+// ---------------------------------------------------------------------------------------------
+template <int LOGJ, int LOGQ>
+__global__ void __launch_bounds__(kNWF * 32, 2) psf_chain2_fwd_kernel(const Chain2Params p) {
+  using G = Geo<LOGJ, LOGQ, false>;
+  constexpr int J = G::J, Q = G::Q, NQ = G::NQ, kNW = G::NW;
+  constexpr int PFW = 4;  // W registers in flight (taps)
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* state = reinterpret_cast<float*>(smem_raw);
+  const uint32_t state_u32 = smem_u32(state);
+  const uint32_t vbar = state_u32 + (uint32_t)(CT * J) * 4u;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x & (Q - 1);
+  const int cid = blockIdx.x >> LOGQ;
+  const int ncl = gridDim.x >> LOGQ;
+  constexpr int n = J * Q;
+  constexpr long long plane = (long long)CT * n;  // floats per sample per state
+  constexpr int blk = CT * J;                     // floats per CTA block
+
+  if (threadIdx.x == 0) {
+    mbar_init(vbar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  uint32_t vparity = 0;
+  bool cw_pending = false;
+
+  for (int b = cid; b < p.B; b += ncl) {
+    float* st0 = p.states + (long long)b * plane;  // slot 0 = V_0 (residual operand, saved state 0)
+    // ---- prologue: V0 rows of this CTA (natural layout) -> state slot 0 ------------------------
+#pragma unroll 1
+    for (int pp = 0; pp < G::NPASS; ++pp) {
+      if (pp * kNW + warp >= G::NT) continue;
+      const int lq = (pp * kNW + warp) * 32 + lane;
+      const int j = 4 * lq;
+      const int i0 = 4 * (lq * Q + q);
+      float4 pl[CT];
+      load_rows_natural(p.Vin + ((long long)b * n + i0) * CT, pl);
+#pragma unroll
+      for (int ch = 0; ch < CT; ++ch) st_cg4(st0 + q * blk + ch * J + j, pl[ch]);
+    }
+    fence_proxy_async();
+    __syncthreads();  // the block is written; nobody reads the shared copy any more
+    if (threadIdx.x == 0) refresh_block<J>(state_u32, vbar, st0 + q * blk);
+    if (Q > 1) {
+      cluster_arrive();
+      cw_pending = true;
+    }
+
+    for (int m = 1; m <= p.n_W; ++m) {
+      const int slot_prev = (p.save_states || m == 1) ? (m - 1) : 1 + ((m - 1) & 1);
+      const int slot_next = p.save_states ? m : 1 + (m & 1);
+      const float* prev = p.states + ((long long)slot_prev * p.B + b) * plane;
+      float* next = p.states + ((long long)slot_next * p.B + b) * plane;
+      const bool last = (m == p.n_W);
+      const float* Wmb = p.W + (long long)(m - 1) * p.sWf + (long long)b * p.sWb + q * J;
+
+      mbar_wait(vbar, vparity);  // V_{m-1} block has landed in shared memory
+      vparity ^= 1u;
+
+#pragma unroll 1
+      for (int pp = 0; pp < G::NPASS; ++pp) {
+        const int tile = pp * kNW + warp;
+        if (tile >= G::NT) continue;  // warp-uniform; pass 0 is full, so every warp executes the cluster wait
+        const int lq = tile * 32 + lane;
+        const int j = 4 * lq;
+        const float* wrow = Wmb + j;
+
+        // ---- L2 prefetch of the W lines this warp reads one pass from now ----------------------
+        if (!(p.dbg & 1)) {
+          int np = pp + 1, nm = m, nb = b;
+          if (np == G::NPASS) {
+            np = 0;
+            if (++nm > p.n_W) {
+              nm = 1;
+              nb = b + ncl;
+            }
+          }
+          if (nb < p.B && np * kNW + warp < G::NT) {
+            const float* nbase = p.W + (long long)(nm - 1) * p.sWf + (long long)nb * p.sWb + q * J +
+                                 (np * kNW + warp) * kTileRows;
+            for (int it = lane; it < G::L * 4; it += 32) prefetch_l2(nbase + (long long)(it >> 2) * p.sWt + (it & 3) * 32);
+          }
+        }
+
+        float4 acc[CT];
+        float4 R[CT];
+        float4 wr[PFW];
+#pragma unroll
+        for (int ch = 0; ch < CT; ++ch) acc[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+        static_for<0, PFW>([&](auto I) {
+          constexpr int i = decltype(I)::value;
+          wr[i] = ldg_w4(wrow + (long long)G::k_at(i) * p.sWt);
+        });
+        if (p.residual) {  // own rows of V_0: written by this very thread in the prologue
+#pragma unroll
+          for (int ch = 0; ch < CT; ++ch) R[ch] = ldcg4_v(st0 + q * blk + ch * J + j);
+        }
+
+        // take the W registers of sequence position idx and refill the slot PFW taps ahead
+        auto take_w = [&](auto I) -> float4 {
+          constexpr int idx = decltype(I)::value;
+          const float4 w = wr[idx % PFW];
+          if constexpr (idx + PFW < G::SEQ) wr[idx % PFW] = ldg_w4(wrow + (long long)G::k_at(idx + PFW) * p.sWt);
+          return w;
+        };
+        auto issue_R = [&](auto Rr) {
+          if constexpr (G::NREM > 0) {
+            constexpr int x = 1 << decltype(Rr)::value;
+            const int qp = (q + x) & (Q - 1);
+            const int lqp = (lq + ((q + x) >> LOGQ)) & (NQ - 1);
+            const float* src = prev + qp * blk + 4 * lqp;
+#pragma unroll
+            for (int ch = 0; ch < CT; ++ch) R[ch] = ldcg4_v(src + ch * J);
+          }
+        };
+
+        static_for<0, G::NGRP>([&](auto Gi) {
+          constexpr int g = decltype(Gi)::value;
+          // ---- plain local taps of this group -----------------------------------------------
+          static_for<G::plo(g), G::plo(g + 1)>([&](auto Pi) {
+            constexpr int pidx = decltype(Pi)::value;
+            constexpr int k = G::kloc(pidx);
+            constexpr int d = 4 << (k - 3 - G::NREM);
+            const float4 w = take_w(IC<G::idx_of(k)>{});
+            const float* vp = state + ((j + d) & (J - 1));
+            float4 v[CT];
+#pragma unroll
+            for (int ch = 0; ch < CT; ++ch) v[ch] = lds4(vp + ch * J);
+#pragma unroll
+            for (int ch = 0; ch < CT; ++ch) fma4(acc[ch], w, v[ch]);
+          });
+          if constexpr (g == 0) {
+            if (p.residual) {
+#pragma unroll
+              for (int ch = 0; ch < CT; ++ch) add4(acc[ch], R[ch]);
+            }
+            if (Q > 1 && cw_pending) {  // siblings have published V_{m-1}
+              cluster_wait();
+              cw_pending = false;
+            }
+            issue_R(IC<0>{});
+          } else if constexpr (g == 1) {
+            // ---- head: offsets 0, 1, 2 and tap 3 share the quads A = own rows, Rq = next quad ----
+            const float4 w0 = take_w(IC<G::idx_of(0)>{});
+            const float4 w1 = take_w(IC<G::idx_of(1)>{});
+            const float4 w2 = take_w(IC<G::idx_of(2)>{});
+            const float4 w3 = take_w(IC<G::idx_of(3)>{});
+#pragma unroll
+            for (int ch = 0; ch < CT; ++ch) {
+              const float4 A = lds4(state + ch * J + j);
+              float4 Rq;
+              if constexpr (G::NREM > 0) Rq = R[ch]; else Rq = lds4(state + ch * J + ((j + 4) & (J - 1)));
+              // row r: w0[r]*V[r] + w1[r]*V[r+1] + w2[r]*V[r+2] + w3[r]*V[r+4]
+              fma4(acc[ch], w0, A);
+              fma4(acc[ch], w3, Rq);
+              fma2(acc[ch].x, acc[ch].y, w2.x, w2.y, A.z, A.w);
+              fma2(acc[ch].z, acc[ch].w, w2.z, w2.w, Rq.x, Rq.y);
+              acc[ch].x = fmaf(w1.x, A.y, acc[ch].x);
+              acc[ch].y = fmaf(w1.y, A.z, acc[ch].y);
+              acc[ch].z = fmaf(w1.z, A.w, acc[ch].z);
+              acc[ch].w = fmaf(w1.w, Rq.x, acc[ch].w);
+            }
+            if constexpr (1 < G::NR) issue_R(IC<1>{});
+          } else {
+            constexpr int r = g - 1;
+            const float4 w = take_w(IC<G::idx_of(3 + r)>{});
+#pragma unroll
+            for (int ch = 0; ch < CT; ++ch) fma4(acc[ch], w, R[ch]);
+            if constexpr (g < G::NR) issue_R(IC<g>{});
+          }
+        });
+
+        if (!last) {
+#pragma unroll
+          for (int ch = 0; ch < CT; ++ch) st_cg4(next + q * blk + ch * J + j, acc[ch]);
+        } else {
+          store_rows_natural(p.Vout + ((long long)b * n + 4 * (lq * Q + q)) * CT, acc);
+        }
+      }
+      if (!last) {
+        fence_proxy_async();
+        __syncthreads();  // all reads of the shared block and all writes of V_m are done
+        if (threadIdx.x == 0) refresh_block<J>(state_u32, vbar, next + q * blk);
+        if (Q > 1) {
+          cluster_arrive();  // V_m visible cluster-wide once the (deferred) wait returns
+          cw_pending = true;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward (output-stationary at row j):
+//   dV_{m-1}[j,:] += W_m[j-o,k] * G_m[j-o,:]      dW_m[j-o,k] = <G_m[j-o,:], V_{m-1}[j,:]>
+// one shifted read of G feeds both; V_{m-1}[j,:] (saved by the forward pass) sits in registers.
+// ---------------------------------------------------------------------------------------------
+template <int LOGJ, int LOGQ>
+__global__ void __launch_bounds__(kNWB * 32, 2) psf_chain2_bwd_kernel(const Chain2Params p) {
+  using G = Geo<LOGJ, LOGQ, true>;
+  constexpr int J = G::J, Q = G::Q, NQ = G::NQ, kNW = G::NW;
+  constexpr int PFW = 3;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* state = reinterpret_cast<float*>(smem_raw);
+  const uint32_t state_u32 = smem_u32(state);
+  const uint32_t vbar = state_u32 + (uint32_t)(CT * J) * 4u;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x & (Q - 1);
+  const int cid = blockIdx.x >> LOGQ;
+  const int ncl = gridDim.x >> LOGQ;
+  constexpr int n = J * Q;
+  constexpr long long plane = (long long)CT * n;
+  constexpr int blk = CT * J;
+
+  if (threadIdx.x == 0) {
+    mbar_init(vbar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  uint32_t vparity = 0;
+  bool cw_pending = false;
+
+  // exchange / residual buffers are per CLUSTER (reused sample after sample) so that they stay in L2
+  float* gx0 = p.gx + (long long)cid * plane;
+  float* gx1 = p.gx + ((long long)ncl + cid) * plane;
+  float* racc = p.racc + (long long)cid * plane + q * blk;
+
+  for (int b = cid; b < p.B; b += ncl) {
+    // ---- prologue: dOut rows of this CTA -> exchange slot 0 ------------------------------------
+#pragma unroll 1
+    for (int pp = 0; pp < G::NPASS; ++pp) {
+      if (pp * kNW + warp >= G::NT) continue;
+      const int lq = (pp * kNW + warp) * 32 + lane;
+      const int j = 4 * lq;
+      const int i0 = 4 * (lq * Q + q);
+      float4 pl[CT];
+      load_rows_natural(p.Vin + ((long long)b * n + i0) * CT, pl);
+#pragma unroll
+      for (int ch = 0; ch < CT; ++ch) st_cg4(gx0 + q * blk + ch * J + j, pl[ch]);
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (threadIdx.x == 0) refresh_block<J>(state_u32, vbar, gx0 + q * blk);
+    if (Q > 1) {
+      cluster_arrive();
+      cw_pending = true;
+    }
+
+    for (int m = p.n_W; m >= 1; --m) {
+      const int step = p.n_W - m;
+      const float* gcur = (step & 1) ? gx1 : gx0;
+      float* gnext = (step & 1) ? gx0 : gx1;
+      const float* vprev = p.states + ((long long)(m - 1) * p.B + b) * plane + q * blk;  // V_{m-1}, own block
+      const float* Wmb = p.W + (long long)(m - 1) * p.sWf + (long long)b * p.sWb;         // sample base
+      float* dWmb = p.dW + (long long)(m - 1) * p.sWf + (long long)b * p.sWb;
+      const bool last = (m == 1);
+      const bool first = (m == p.n_W);
+
+      mbar_wait(vbar, vparity);  // G_m block has landed in shared memory
+      vparity ^= 1u;
+
+#pragma unroll 1
+      for (int pp = 0; pp < G::NPASS; ++pp) {
+        const int tile = pp * kNW + warp;
+        if (tile >= G::NT) continue;  // warp-uniform; pass 0 is full, so every warp executes the cluster wait
+        const int lq = tile * 32 + lane;
+        const int j = 4 * lq;
+
+        // position (inside one tap plane of the sample) of the W / dW quad that tap k pairs with row quad lq
+        auto wpos = [&](auto K) -> int {
+          constexpr int k = decltype(K)::value;
+          if constexpr (k < 3) {
+            return q * J + j;
+          } else if constexpr (k < 3 + G::NREM) {
+            constexpr int x = 1 << (k - 3);
+            const int qp = (q - x) & (Q - 1);
+            const int lqp = (lq - (q < x ? 1 : 0)) & (NQ - 1);
+            return qp * J + 4 * lqp;
+          } else {
+            constexpr int d = 4 << (k - 3 - G::NREM);
+            return q * J + ((j - d) & (J - 1));
+          }
+        };
+
+        // ---- L2 prefetch: W windows and V_{m-1} rows this warp reads one pass from now ----------
+        if (!(p.dbg & 1)) {
+          int np = pp + 1, nm = m, nb = b;
+          if (np == G::NPASS) {
+            np = 0;
+            if (--nm < 1) {
+              nm = p.n_W;
+              nb = b + ncl;
+            }
+          }
+          if (nb < p.B && np * kNW + warp < G::NT) {
+            const float* nW = p.W + (long long)(nm - 1) * p.sWf + (long long)nb * p.sWb;
+            const int j0 = (np * kNW + warp) * kTileRows;
+            // items: (tap k, line 0..4); taps 1,2 additionally need the window of tap 3 (previous quad)
+            for (int it = lane; it < (G::L + 2) * 5; it += 32) {
+              int k = it / 5;
+              const int line = it - k * 5;
+              int kk = k;  // geometry of the window
+              if (k >= G::L) {
+                kk = 3;
+                k = k - G::L + 1;
+              }
+              int bq = q, shift = 0;
+              if (kk >= 3 && kk < 3 + G::NREM) {
+                const int x = 1 << (kk - 3);
+                bq = (q - x) & (Q - 1);
+                shift = (q < x) ? 4 : 0;
+              } else if (kk >= 3) {
+                shift = 4 << (kk - 3 - G::NREM);
+              }
+              const int start = ((j0 - shift) & (J - 1)) & ~31;
+              prefetch_l2(nW + (long long)k * p.sWt + bq * J + ((start + 32 * line) & (J - 1)));
+            }
+            const float* nV = p.states + ((long long)(nm - 1) * p.B + nb) * plane + q * blk + j0;
+            prefetch_l2(nV + (lane >> 2) * J + (lane & 3) * 32);
+          }
+        }
+
+        float4 acc[CT];
+        float4 vown[CT];
+        float4 R[CT];
+        float4 wr[PFW];
+#pragma unroll
+        for (int ch = 0; ch < CT; ++ch) acc[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int ch = 0; ch < CT; ++ch) vown[ch] = __ldcs(reinterpret_cast<const float4*>(vprev + ch * J + j));
+        static_for<0, PFW>([&](auto I) {
+          constexpr int i = decltype(I)::value;
+          constexpr int k = G::k_at(i);
+          wr[i] = ldg_w4(Wmb + (long long)k * p.sWt + wpos(IC<k>{}));
+        });
+        auto take_w = [&](auto I) -> float4 {
+          constexpr int idx = decltype(I)::value;
+          const float4 w = wr[idx % PFW];
+          if constexpr (idx + PFW < G::SEQ) {
+            constexpr int kn = G::k_at(idx + PFW);
+            wr[idx % PFW] = ldg_w4(Wmb + (long long)kn * p.sWt + wpos(IC<kn>{}));
+          }
+          return w;
+        };
+        // W of taps 1, 2 straddles the own quad (rows lo >= offset) and the previous quad
+        float4 w1a;
+        float2 w2a, w2r;
+        float w1r;
+        const int pos_own = q * J + j;
+        const int pos_r0 = wpos(IC<3>{});  // quad u-1: remote CTA q-1 (or local quad lq-1 without a cluster)
+        auto issue_R = [&](auto Rr) {
+          constexpr int r = decltype(Rr)::value;
+          if constexpr (G::NREM > 0) {
+            constexpr int x = 1 << r;
+            const int qp = (q - x) & (Q - 1);
+            const int lqp = (lq - (q < x ? 1 : 0)) & (NQ - 1);
+            const float* src = gcur + qp * blk + 4 * lqp;
+#pragma unroll
+            for (int ch = 0; ch < CT; ++ch) R[ch] = ldcg4_v(src + ch * J);
+          }
+          if constexpr (r == 0) {
+            w1a = ldg_w4(Wmb + p.sWt + pos_own);
+            w1r = ldg_w1(Wmb + p.sWt + pos_r0 + 3);
+            w2a = ldg_w2(Wmb + 2 * p.sWt + pos_own);
+            w2r = ldg_w2(Wmb + 2 * p.sWt + pos_r0 + 2);
+          }
+        };
+        // one aligned tap: operand quads g[ch], W quad w, dW quad stored at `pos` of tap k
+        auto tap = [&](const float4 (&g)[CT], const float4& w, int k, int pos) {
+          float4 dw = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int ch = 0; ch < CT; ++ch) {
+            fma4(acc[ch], w, g[ch]);
+            fma4(dw, g[ch], vown[ch]);
+          }
+          st_cs4(dWmb + (long long)k * p.sWt + pos, dw);
+        };
+
+        static_for<0, G::NGRP>([&](auto Gi) {
+          constexpr int g = decltype(Gi)::value;
+          static_for<G::plo(g), G::plo(g + 1)>([&](auto Pi) {
+            constexpr int pidx = decltype(Pi)::value;
+            constexpr int k = G::kloc(pidx);
+            constexpr int d = 4 << (k - 3 - G::NREM);
+            const float4 w = take_w(IC<G::idx_of(k)>{});
+            const int js = (j - d) & (J - 1);
+            float4 v[CT];
+#pragma unroll
+            for (int ch = 0; ch < CT; ++ch) v[ch] = lds4(state + ch * J + js);
+            tap(v, w, k, q * J + js);
+          });
+          if constexpr (g == 0) {
+            if (Q > 1 && cw_pending) {
+              cluster_wait();
+              cw_pending = false;
+            }
+            issue_R(IC<0>{});
+          } else if constexpr (g == 1) {
+            // ---- head: tap 3 on the previous quad Rq, then taps 0, 1, 2 on (Rq, own quad A) ----
+            const float4 w3 = take_w(IC<G::idx_of(3)>{});
+            const float4 w0 = take_w(IC<G::idx_of(0)>{});
+            if constexpr (G::NREM == 0) {
+#pragma unroll
+              for (int ch = 0; ch < CT; ++ch) R[ch] = lds4(state + ch * J + ((j - 4) & (J - 1)));
+            }
+            tap(R, w3, 3, pos_r0);
+            const float4 w1 = make_float4(w1r, w1a.x, w1a.y, w1a.z);
+            const float4 w2 = make_float4(w2r.x, w2r.y, w2a.x, w2a.y);
+            float4 dw0 = make_float4(0.f, 0.f, 0.f, 0.f), dw1 = dw0, dw2 = dw0;
+#pragma unroll
+            for (int ch = 0; ch < CT; ++ch) {
+              const float4 A = lds4(state + ch * J + j);
+              const float4 g1 = make_float4(R[ch].w, A.x, A.y, A.z);   // rows j-1 .. j+2
+              const float4 g2 = make_float4(R[ch].z, R[ch].w, A.x, A.y);  // rows j-2 .. j+1
+              fma4(acc[ch], w0, A);
+              fma4(dw0, A, vown[ch]);
+              fma4(acc[ch], w1, g1);
+              fma4(dw1, g1, vown[ch]);
+              fma4(acc[ch], w2, g2);
+              fma4(dw2, g2, vown[ch]);
+            }
+            float* d0 = dWmb + pos_own;
+            st_cs4(d0, dw0);
+            float* d1 = dWmb + p.sWt;
+            __stcs(d1 + pos_r0 + 3, dw1.x);
+            st_cs2(d1 + pos_own, dw1.y, dw1.z);
+            __stcs(d1 + pos_own + 2, dw1.w);
+            float* d2 = dWmb + 2 * p.sWt;
+            st_cs2(d2 + pos_r0 + 2, dw2.x, dw2.y);
+            st_cs2(d2 + pos_own, dw2.z, dw2.w);
+            if constexpr (1 < G::NR) issue_R(IC<1>{});
+          } else {
+            constexpr int r = g - 1;
+            const float4 w = take_w(IC<G::idx_of(3 + r)>{});
+            tap(R, w, 3 + r, wpos(IC<3 + r>{}));
+            if constexpr (g < G::NR) issue_R(IC<g>{});
+          }
+        });
+
+        // residual: dV0 also receives G_m of every factor (V_m = W_m V_{m-1} + V_0)
+        if (p.residual) {
+#pragma unroll
+          for (int ch = 0; ch < CT; ++ch) {
+            float4 own = lds4(state + ch * J + j);
+            if (!first) add4(own, ldcg4_v(racc + ch * J + j));
+            if (!last) {
+              st_cg4(racc + ch * J + j, own);
+            } else {
+              add4(acc[ch], own);
+            }
+          }
+        }
+        if (!last) {
+#pragma unroll
+          for (int ch = 0; ch < CT; ++ch) st_cg4(gnext + q * blk + ch * J + j, acc[ch]);
+        } else {
+          store_rows_natural(p.Vout + ((long long)b * n + 4 * (lq * Q + q)) * CT, acc);
+        }
+      }
+      if (!last) {
+        fence_proxy_async();
+        __syncthreads();
+        if (threadIdx.x == 0) refresh_block<J>(state_u32, vbar, gnext + q * blk);
+        if (Q > 1) {
+          cluster_arrive();
+          cw_pending = true;
+        }
+      }
+    }
+    // the exchange buffers belong to the cluster: the next sample may overwrite them only after every
+    // CTA has finished reading this sample's last state
+    if (Q > 1) {
+      cluster_arrive();
+      cluster_wait();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+constexpr int kLogJ = 11;
+
+int env_int2(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  if (v == nullptr || *v == 0) return dflt;
+  return std::atoi(v);
+}
+
+const void* fwd2_kernel_for(int logq) {
+  switch (logq) {
+    case 0: return (const void*)psf_chain2_fwd_kernel<kLogJ, 0>;
+    case 1: return (const void*)psf_chain2_fwd_kernel<kLogJ, 1>;
+    case 2: return (const void*)psf_chain2_fwd_kernel<kLogJ, 2>;
+    default: return (const void*)psf_chain2_fwd_kernel<kLogJ, 3>;
+  }
+}
+const void* bwd2_kernel_for(int logq) {
+  switch (logq) {
+    case 0: return (const void*)psf_chain2_bwd_kernel<kLogJ, 0>;
+    case 1: return (const void*)psf_chain2_bwd_kernel<kLogJ, 1>;
+    case 2: return (const void*)psf_chain2_bwd_kernel<kLogJ, 2>;
+    default: return (const void*)psf_chain2_bwd_kernel<kLogJ, 3>;
+  }
+}
+
+constexpr int kSmem2 = CT * (1 << kLogJ) * 4 + 64;
+
+bool g_attr2_done = false;
+int g_res2[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+
+int resident2(bool bwd, int logq) {
+  int& slot = g_res2[bwd ? 1 : 0][logq];
+  if (slot > 0) return slot;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const void* kernel = bwd ? bwd2_kernel_for(logq) : fwd2_kernel_for(logq);
+  const int Q = 1 << logq;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(Q * sms * 2), 1, 1);
+  cfg.blockDim = dim3((unsigned)((bwd ? kNWB : kNWF) * 32), 1, 1);
+  cfg.dynamicSmemBytes = (size_t)kSmem2;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)Q;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int ncl = 0;
+  if (cudaOccupancyMaxActiveClusters(&ncl, kernel, &cfg) != cudaSuccess || ncl < 1) {
+    cudaGetLastError();
+    return 0;
+  }
+  slot = ncl;
+  return ncl;
+}
+
+int launch2(const void* kernel, const Chain2Params& cp, int logq, int resident, int threads, cudaStream_t st) {
+  const int Q = 1 << logq;
+  cudaLaunchConfig_t cfg = {};
+  const int clusters = resident < cp.B ? resident : cp.B;
+  cfg.gridDim = dim3((unsigned)(clusters * Q), 1, 1);
+  cfg.blockDim = dim3((unsigned)threads, 1, 1);
+  cfg.dynamicSmemBytes = (size_t)kSmem2;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)Q;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  void* args[] = {(void*)&cp};
+  return (int)cudaLaunchKernelExC(&cfg, kernel, args);
+}
+
+void fill2(Chain2Params& cp, const PsfChainArgs& a) {
+  cp.sWf = a.ws.factor;
+  cp.sWb = a.ws.sample;
+  cp.sWt = a.ws.tap;
+  cp.B = (int)a.B;
+  cp.n_W = a.n_W;
+  cp.residual = a.residual;
+  cp.dbg = env_int2("PSF_CHAIN2_DEBUG", 0);
+}
+
+}  // namespace
+
+// Row interleave (cluster size Q) the second-generation kernels want for this problem, or 0 if they do
+// not cover it.  Shape rules only; layout/pointer checks are psf_chain2_plan's.
+int psf_chain2_interleave_for(const PsfChainArgs& a) {
+  if (env_int2("PSF_CHAIN_V2", 1) == 0) return 0;
+  if (a.C != CT || a.n_W < 1 || a.B < 1 || a.B > (1 << 20)) return 0;
+  int logn = 0;
+  while ((int64_t(1) << logn) < a.n) ++logn;
+  if ((int64_t(1) << logn) != a.n || logn < kLogJ || logn > kLogJ + 3) return 0;
+  if (a.L != logn + 1) return 0;
+  for (int k = 0; k < a.L; ++k)
+    if (a.offs.o[k] != (k == 0 ? 0 : (1 << (k - 1)))) return 0;
+  return 1 << (logn - kLogJ);
+}
+
+int psf_chain2_plan(const PsfChainArgs& a, PsfFusedPlan* plan) {
+  const int Q = psf_chain2_interleave_for(a);
+  if (Q == 0) return PSF_ERR_UNSUPPORTED;
+  const int il = a.interleave < 1 ? 1 : a.interleave;
+  if (il != Q) return PSF_ERR_UNSUPPORTED;
+  if (a.ws.row != 1 || (a.ws.factor & 3) || (a.ws.sample & 3) || (a.ws.tap & 3)) return PSF_ERR_UNSUPPORTED;
+  int logq = 0;
+  while ((1 << logq) < Q) ++logq;
+  if (!g_attr2_done) {
+    for (int lq = 0; lq < 4; ++lq)
+      if (cudaFuncSetAttribute(fwd2_kernel_for(lq), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2) != cudaSuccess ||
+          cudaFuncSetAttribute(bwd2_kernel_for(lq), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2) != cudaSuccess) {
+        cudaGetLastError();
+        return PSF_ERR_UNSUPPORTED;
+      }
+    g_attr2_done = true;
+  }
+  const int rf = resident2(false, logq), rb = resident2(true, logq);
+  if (rf < 1 || rb < 1) return PSF_ERR_UNSUPPORTED;
+  plan->cluster = Q;
+  plan->rows_per_cta = 1 << kLogJ;
+  plan->threads = kNWF * 32;
+  plan->smem_bytes = kSmem2;
+  plan->smem_bytes_bwd = kSmem2;
+  plan->resident = rf;
+  plan->resident_bwd = rb;
+  plan->stages = 0;
+  plan->stages_bwd = 0;
+  return PSF_OK;
+}
+
+// Workspace (floats, S = B*n*8):  states [0, n_W*S) (save) or [0, 3*S);  then gx 2*S, racc S (backward only).
+int psf_chain2_fwd(const PsfChainArgs& a, const float* W, const float* V0, float* out, float* ws, int save_states,
+                   cudaStream_t st) {
+  PsfFusedPlan plan;
+  int rc = psf_chain2_plan(a, &plan);
+  if (rc) return rc;
+  int logq = 0;
+  while ((1 << logq) < plan.cluster) ++logq;
+  Chain2Params cp = {};
+  cp.W = W;
+  cp.Vin = V0;
+  cp.Vout = out;
+  cp.states = ws;
+  cp.save_states = save_states;
+  fill2(cp, a);
+  return launch2(fwd2_kernel_for(logq), cp, logq, plan.resident, kNWF * 32, st);
+}
+
+int psf_chain2_bwd(const PsfChainArgs& a, const float* W, const float* dOut, float* dW, float* dV0, float* ws,
+                   cudaStream_t st) {
+  PsfFusedPlan plan;
+  int rc = psf_chain2_plan(a, &plan);
+  if (rc) return rc;
+  int logq = 0;
+  while ((1 << logq) < plan.cluster) ++logq;
+  const long long S = a.B * a.n * a.C;
+  Chain2Params cp = {};
+  cp.W = W;
+  cp.dW = dW;
+  cp.Vin = dOut;
+  cp.Vout = dV0;
+  cp.states = ws;
+  cp.gx = ws + (long long)a.n_W * S;
+  cp.racc = cp.gx + 2 * S;
+  cp.save_states = 1;
+  fill2(cp, a);
+  return launch2(bwd2_kernel_for(logq), cp, logq, plan.resident_bwd, kNWB * 32, st);
+}

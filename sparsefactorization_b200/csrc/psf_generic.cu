@@ -96,10 +96,18 @@ __global__ void __launch_bounds__(kThreads) add_kernel(T* __restrict__ acc, cons
     acc[idx] = y ? x[idx] + y[idx] : x[idx];
 }
 
+// physical position of logical row i on a quad-interleaved row axis (psf_b200.h): quads u = i>>2 are dealt
+// round-robin to Q blocks of n/Q rows
+__device__ __forceinline__ int64_t row_pos(int64_t i, int64_t n, int Q) {
+  if (Q <= 1) return i;
+  const int64_t u = i >> 2;
+  return (u % Q) * (n / Q) + 4 * (u / Q) + (i & 3);
+}
+
 template <typename T>
-__global__ void __launch_bounds__(kThreads) relayout_kernel(const T* __restrict__ src, psf_wstrides ss,
-                                                            T* __restrict__ dst, psf_wstrides ds, int n_W, int64_t B,
-                                                            int64_t n, int L) {
+__global__ void __launch_bounds__(kThreads) relayout_kernel(const T* __restrict__ src, psf_wstrides ss, int qs,
+                                                            T* __restrict__ dst, psf_wstrides ds, int qd, int n_W,
+                                                            int64_t B, int64_t n, int L) {
   // 32 rows x L taps tile through shared memory so that both sides see their contiguous axis.
   extern __shared__ unsigned char smem_raw[];
   T* tile = reinterpret_cast<T*>(smem_raw);  // [32][L+1]
@@ -118,13 +126,13 @@ __global__ void __launch_bounds__(kThreads) relayout_kernel(const T* __restrict_
     for (int e = threadIdx.x; e < elems; e += blockDim.x) {
       int r, k;
       if (ss.tap <= ss.row) { k = e % L; r = e / L; } else { r = e % 32; k = e / 32; }
-      if (r0 + r < n) tile[r * (L + 1) + k] = s[(r0 + r) * ss.row + k * ss.tap];
+      if (r0 + r < n) tile[r * (L + 1) + k] = s[row_pos(r0 + r, n, qs) * ss.row + k * ss.tap];
     }
     __syncthreads();
     for (int e = threadIdx.x; e < elems; e += blockDim.x) {
       int r, k;
       if (ds.tap <= ds.row) { k = e % L; r = e / L; } else { r = e % 32; k = e / 32; }
-      if (r0 + r < n) d[(r0 + r) * ds.row + k * ds.tap] = tile[r * (L + 1) + k];
+      if (r0 + r < n) d[row_pos(r0 + r, n, qd) * ds.row + k * ds.tap] = tile[r * (L + 1) + k];
     }
     __syncthreads();
   }
@@ -216,17 +224,17 @@ int psf_generic_chain_bwd(const PsfChainArgs& a, const T* W, const T* dOut, T* d
   return PSF_OK;
 }
 
-int psf_generic_relayout(psf_dtype dtype, const void* src, psf_wstrides ss, void* dst, psf_wstrides ds, int n_W,
-                         int64_t B, int64_t n, int L, cudaStream_t st) {
+int psf_generic_relayout(psf_dtype dtype, const void* src, psf_wstrides ss, int qs, void* dst, psf_wstrides ds, int qd,
+                         int n_W, int64_t B, int64_t n, int L, cudaStream_t st) {
   if ((int64_t)n_W * B * n * L == 0) return PSF_OK;
   const int64_t tiles = (int64_t)n_W * B * ((n + 31) / 32);
   const int grid = (int)(tiles > 148 * 16 ? 148 * 16 : tiles);
   if (dtype == PSF_F32) {
-    relayout_kernel<float><<<grid, 256, 32 * (L + 1) * sizeof(float), st>>>((const float*)src, ss, (float*)dst, ds, n_W,
-                                                                            B, n, L);
+    relayout_kernel<float><<<grid, 256, 32 * (L + 1) * sizeof(float), st>>>((const float*)src, ss, qs, (float*)dst, ds, qd,
+                                                                            n_W, B, n, L);
   } else {
-    relayout_kernel<double><<<grid, 256, 32 * (L + 1) * sizeof(double), st>>>((const double*)src, ss, (double*)dst, ds,
-                                                                              n_W, B, n, L);
+    relayout_kernel<double><<<grid, 256, 32 * (L + 1) * sizeof(double), st>>>((const double*)src, ss, qs, (double*)dst,
+                                                                              ds, qd, n_W, B, n, L);
   }
   return (int)cudaGetLastError();
 }

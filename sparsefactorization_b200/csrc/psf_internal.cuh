@@ -21,6 +21,7 @@ struct PsfChainArgs {
   int n_W, L, residual;
   psf_wstrides ws;
   PsfOffsets offs;
+  int interleave;  // row order of W/dW: 1 natural, Q > 1 quad-interleaved (see psf_b200.h)
 };
 
 static inline size_t psf_round256(size_t x) { return (x + 255) & ~size_t(255); }
@@ -39,8 +40,8 @@ int psf_generic_factor_dW(const T* dZ, const T* V, T* dWm, int64_t s_sample, int
 template <typename T>
 int psf_generic_axpy(T* acc, const T* x, const T* y, int64_t count, cudaStream_t st);  // acc = x + y (y may be null)
 
-int psf_generic_relayout(psf_dtype dtype, const void* src, psf_wstrides ss, void* dst, psf_wstrides ds, int n_W,
-                         int64_t B, int64_t n, int L, cudaStream_t st);
+int psf_generic_relayout(psf_dtype dtype, const void* src, psf_wstrides ss, int src_interleave, void* dst,
+                         psf_wstrides ds, int dst_interleave, int n_W, int64_t B, int64_t n, int L, cudaStream_t st);
 
 template <typename T>
 int psf_generic_chain_fwd(const PsfChainArgs& a, const T* W, const T* V0, T* out, T* ws, int save_states,
@@ -66,3 +67,11 @@ int psf_fused_chain_fwd(const PsfChainArgs& a, const float* W, const float* V0, 
                         int save_states, cudaStream_t st);
 int psf_fused_chain_bwd(const PsfChainArgs& a, const float* W, const float* dOut, float* dW, float* dV0, float* ws,
                         cudaStream_t st);
+
+// ---- second-generation fused kernels (quad-interleaved clusters, see psf_chain2_sm100.cu) ---
+int psf_chain2_interleave_for(const PsfChainArgs& a);           // Q the kernels want for this shape, 0 = not covered
+int psf_chain2_plan(const PsfChainArgs& a, PsfFusedPlan* plan);  // PSF_OK iff shape, layout and a.interleave fit
+int psf_chain2_fwd(const PsfChainArgs& a, const float* W, const float* V0, float* out, float* ws, int save_states,
+                   cudaStream_t st);
+int psf_chain2_bwd(const PsfChainArgs& a, const float* W, const float* dOut, float* dW, float* dV0, float* ws,
+                   cudaStream_t st);

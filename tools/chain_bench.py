@@ -42,27 +42,32 @@ def main():
     ap.add_argument("--path", default="auto")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--peak", type=float, default=6450.3)
+    ap.add_argument("--gen", type=int, default=2, help="fused kernel generation: 2 = quad-interleaved W rows, 1 = natural")
     a = ap.parse_args()
     n_W = a.n_W or (a.n - 1).bit_length()
     L = n_W + 1
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev).manual_seed(0)
+    Q = chain.preferred_interleave(n_W, a.B, a.n, L, a.C) if a.gen == 2 and a.path == "auto" else 1
+    if a.gen == 1 and a.path == "auto":
+        a.path = "fused_gen1"
     W = chain.empty_tap_major(n_W, a.B, a.n, L, device=dev)
     W.copy_(0.25 * torch.randn(n_W, a.B, a.n, L, generator=g, device=dev) / L ** 0.5)
     W.requires_grad_(True)
     V0 = torch.randn(a.B, a.n, a.C, generator=g, device=dev).requires_grad_(True)
     dOut = torch.randn(a.B, a.n, a.C, generator=g, device=dev)
-    plan = chain.fused_plan(n_W, a.B, a.n, L, a.C, bool(a.residual))
+    plan = chain.fused_plan(n_W, a.B, a.n, L, a.C, bool(a.residual), interleave=Q, path=a.path)
+    gen = chain.fused_generation(n_W, a.B, a.n, L, a.C, interleave=Q, path=a.path)
     fb, bb = alg_bytes(a.n, n_W, L, a.C)
 
     def fwd_nograd():
         with torch.no_grad():
-            chain.chord_chain(W, V0, bool(a.residual), path=a.path)
+            chain.chord_chain(W, V0, bool(a.residual), path=a.path, interleave=Q)
 
     holder = {}
 
     def fwd():
-        holder["out"] = chain.chord_chain(W, V0, bool(a.residual), path=a.path)
+        holder["out"] = chain.chord_chain(W, V0, bool(a.residual), path=a.path, interleave=Q)
 
     def bwd():
         W.grad = None
@@ -74,7 +79,7 @@ def main():
     used = chain.last_path_used
     t_bwd, _ = time_ms(bwd, a.iters)
     res = {
-        "n": a.n, "B": a.B, "C": a.C, "n_W": n_W, "path": used, "plan": plan,
+        "n": a.n, "B": a.B, "C": a.C, "n_W": n_W, "path": used, "generation": gen, "interleave": Q, "plan": plan,
         "fwd_nograd_ms": round(t_inf, 4), "fwd_ms": round(t_fwd, 4), "bwd_ms": round(t_bwd, 4),
         "fwd_GBps": round(a.B * fb / t_fwd / 1e6, 1), "bwd_GBps": round(a.B * bb / t_bwd / 1e6, 1),
         "fwdbwd_GBps": round(a.B * (fb + bb) / (t_fwd + t_bwd) / 1e6, 1),
