@@ -73,7 +73,7 @@ def load():
     with _lock:
         if _lib is not None:
             return _lib
-        path = _build.LIB_PATH
+        path = os.environ.get("PSF_B200_LIB") or _build.LIB_PATH   # override: A/B runs of differently tuned builds
         if not os.path.exists(path):
             try:
                 path = _build.build()

@@ -46,21 +46,26 @@ def find_nvcc() -> str:
     raise RuntimeError("nvcc not found (needed to build libpsf_b200.so)")
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = None) -> str:
+    """``defines`` / ``out``: tuning builds (e.g. ``-DPSF2_NW_BWD=6``) written next to the default library and
+    selected at run time with the PSF_B200_LIB environment variable."""
+    out = out or LIB_PATH
+    if not force and out == LIB_PATH and not _stale():
         return LIB_PATH
-    os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [find_nvcc(), *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    cmd = [find_nvcc(), *NVCC_FLAGS, *defines, "-I", os.path.join(ROOT, "include"), "-I", CSRC]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", LIB_PATH, *sources()]
+    cmd += ["-o", out, *sources()]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libpsf_b200.so")
-    return LIB_PATH
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    _out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
+    print(build(force="--force" in sys.argv or _out is not None, verbose="--verbose" in sys.argv,
+                defines=[a for a in sys.argv[1:] if a.startswith("-D")], out=_out))

@@ -19,7 +19,7 @@
 // W / dW stream: physical layout [n_W][L][B][n'] where n' is the row axis in "quad-interleaved"
 // order p(i) = q*J + 4*lq + lo (desc.interleave = Q): each CTA's rows of one tap are one contiguous
 // 8 KB run.  W goes global -> registers directly (coalesced 512 B per warp and tap, read exactly
-// once, prefetched into L2 one pass ahead and into registers a few taps ahead); it does not pass
+// once, prefetched into registers a few taps ahead - an L2 prefetch one pass ahead measured no gain); it does not pass
 // through shared memory, which carries only the V/G operand traffic (the co-critical resource).
 //
 // State handling is the first generation's: the CTA's block of the current state sits in shared
@@ -36,14 +36,33 @@
 
 namespace {
 
-// warps per CTA: the forward pass fits 128 registers (8 warps, 2 CTAs per SM); the backward pass keeps two
-// 32-register operand sets (accumulators and the stationary V_{m-1} rows) and runs 6 warps at 168 registers
+// Launch shape (compile-time knobs): warps per CTA, CTAs per SM, W registers in flight (taps).  The forward pass
+// fits 128 registers (8 warps x 2 CTAs per SM); the backward pass keeps two 32-register operand sets (accumulators
+// and the stationary V_{m-1} rows) and runs 4 warps x 3 CTAs per SM at 168 registers (16 tiles = 4 even passes).
 #ifndef PSF2_NW_FWD
 #define PSF2_NW_FWD 8
 #endif
-#ifndef PSF2_NW_BWD
-#define PSF2_NW_BWD 6
+#ifndef PSF2_MINB_FWD
+#define PSF2_MINB_FWD 2
 #endif
+#ifndef PSF2_PFW_FWD
+#define PSF2_PFW_FWD 4
+#endif
+#ifndef PSF2_NW_BWD
+#define PSF2_NW_BWD 4
+#endif
+#ifndef PSF2_MINB_BWD
+#define PSF2_MINB_BWD 3
+#endif
+#ifndef PSF2_PFW_BWD
+#define PSF2_PFW_BWD 3
+#endif
+// timing experiments only (results become wrong): 1 no W loads, 2 no dW stores, 4 no residual traffic,
+// 8 no V_{m-1} loads, 16 no remote operand loads, 32 no state stores, 64 no cluster barrier
+#ifndef PSF2_ABLATE
+#define PSF2_ABLATE 0
+#endif
+constexpr int kAbl = PSF2_ABLATE;
 constexpr int kNWF = PSF2_NW_FWD;
 constexpr int kNWB = PSF2_NW_BWD;
 constexpr int kTileRows = 128;       // rows per warp tile (32 lanes x one quad)
@@ -79,8 +98,10 @@ __device__ __forceinline__ void static_for(F&& f) {
 //   element offset 4<<t inside the CTA's J rows).
 //   R-quads: the NR = max(NREM,1) quads that are staged in registers: remote taps, or - without a cluster -
 //   the local quad of tap 3, which the offset-1/2 taps need next to the thread's own quad.
-//   Schedule of one pass: plain local taps are split into NR+1 groups; R(0) is issued after group 0,
-//   consumed after group 1 together with taps 0,1,2 ("head"), R(r) is issued when R(r-1) has been consumed.
+//   Schedule of one pass: plain local taps are split into NR+2 groups; R(0) is issued after group 0,
+//   consumed after group 1 together with taps 0,1,2 ("head"), R(r) is issued when R(r-1) has been consumed,
+//   and when the last R-quad is consumed the same registers fetch the residual operand ("tail"), which is
+//   used after the last group.
 //   W registers are loaded in consumption order: idx -> tap k = k_at(idx).  The backward pass loads the
 //   W values of taps 1,2 separately (they straddle two quads), so its sequence skips them.
 template <int LOGJ, int LOGQ, bool BWD>
@@ -97,7 +118,7 @@ struct Geo {
   static constexpr int NR = NREM > 0 ? NREM : 1;
   static constexpr int SKIP0 = NREM > 0 ? 0 : 1;  // local tap 0 is R(0) when there is no cluster
   static constexpr int P = NLOC - SKIP0;          // plain local taps
-  static constexpr int NGRP = NR + 1;
+  static constexpr int NGRP = NR + 2;  // the last group covers the latency of the tail loads (residual operand)
   static constexpr int HEADN = BWD ? 2 : 4;
   static constexpr int SEQ = P + HEADN + (NR - 1);
   __host__ __device__ static constexpr int plo(int g) { return g * P / NGRP; }
@@ -115,7 +136,7 @@ struct Geo {
           if (s == idx) return headk(h);
           ++s;
         }
-      } else if (g >= 2) {
+      } else if (g >= 2 && g <= NR) {
         if (s == idx) return 3 + (g - 1);
         ++s;
       }
@@ -129,21 +150,22 @@ struct Geo {
   }
 };
 
-__device__ __forceinline__ float4 ldg_w4(const float* p) {  // W: read once, keep out of L1
+__device__ __forceinline__ float4 ldg_w4(const float* p) {  // W: read once (streaming: evict-first in L1 and L2)
   float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+  if constexpr (kAbl & 1) return make_float4(0.5f, 0.25f, 0.125f, 1.f);
+  asm volatile("ld.global.cs.v4.f32 {%0, %1, %2, %3}, [%4];"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                : "l"(p));
   return v;
 }
 __device__ __forceinline__ float2 ldg_w2(const float* p) {
   float2 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  asm volatile("ld.global.cs.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
   return v;
 }
 __device__ __forceinline__ float ldg_w1(const float* p) {
   float v;
-  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
 // exchanged state written by sibling CTAs during this kernel: L2-coherent load, pinned in program order
@@ -155,7 +177,25 @@ __device__ __forceinline__ float4 ldcg4_v(const float* p) {
                : "memory");
   return v;
 }
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// exchange buffers of the backward pass (reused by the cluster sample after sample): keep them in L2
+__device__ __forceinline__ unsigned long long make_evict_last_policy() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ldcg4_keep(const float* p, unsigned long long pol) {
+  float4 v;
+  asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(pol)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void stcg4_keep(float* p, const float4& v, unsigned long long pol) {
+  asm volatile("st.global.cg.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w), "l"(pol)
+               : "memory");
+}
 
 __device__ __forceinline__ void st_cs2(float* p, float a, float b) { __stcs(reinterpret_cast<float2*>(p), make_float2(a, b)); }
 
@@ -171,10 +211,10 @@ __device__ __forceinline__ void refresh_block(uint32_t state_u32, uint32_t vbar,
 // Forward
 // ---------------------------------------------------------------------------------------------
 template <int LOGJ, int LOGQ>
-__global__ void __launch_bounds__(kNWF * 32, 2) psf_chain2_fwd_kernel(const Chain2Params p) {
+__global__ void __launch_bounds__(kNWF * 32, PSF2_MINB_FWD) psf_chain2_fwd_kernel(const Chain2Params p) {
   using G = Geo<LOGJ, LOGQ, false>;
   constexpr int J = G::J, Q = G::Q, NQ = G::NQ, kNW = G::NW;
-  constexpr int PFW = 4;  // W registers in flight (taps)
+  constexpr int PFW = PSF2_PFW_FWD;  // W registers in flight (taps)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* state = reinterpret_cast<float*>(smem_raw);
   const uint32_t state_u32 = smem_u32(state);
@@ -213,7 +253,7 @@ __global__ void __launch_bounds__(kNWF * 32, 2) psf_chain2_fwd_kernel(const Chai
     fence_proxy_async();
     __syncthreads();  // the block is written; nobody reads the shared copy any more
     if (threadIdx.x == 0) refresh_block<J>(state_u32, vbar, st0 + q * blk);
-    if (Q > 1) {
+    if (Q > 1 && !(kAbl & 64)) {
       cluster_arrive();
       cw_pending = true;
     }
@@ -237,23 +277,6 @@ __global__ void __launch_bounds__(kNWF * 32, 2) psf_chain2_fwd_kernel(const Chai
         const int j = 4 * lq;
         const float* wrow = Wmb + j;
 
-        // ---- L2 prefetch of the W lines this warp reads one pass from now ----------------------
-        if (!(p.dbg & 1)) {
-          int np = pp + 1, nm = m, nb = b;
-          if (np == G::NPASS) {
-            np = 0;
-            if (++nm > p.n_W) {
-              nm = 1;
-              nb = b + ncl;
-            }
-          }
-          if (nb < p.B && np * kNW + warp < G::NT) {
-            const float* nbase = p.W + (long long)(nm - 1) * p.sWf + (long long)nb * p.sWb + q * J +
-                                 (np * kNW + warp) * kTileRows;
-            for (int it = lane; it < G::L * 4; it += 32) prefetch_l2(nbase + (long long)(it >> 2) * p.sWt + (it & 3) * 32);
-          }
-        }
-
         float4 acc[CT];
         float4 R[CT];
         float4 wr[PFW];
@@ -263,11 +286,6 @@ __global__ void __launch_bounds__(kNWF * 32, 2) psf_chain2_fwd_kernel(const Chai
           constexpr int i = decltype(I)::value;
           wr[i] = ldg_w4(wrow + (long long)G::k_at(i) * p.sWt);
         });
-        if (p.residual) {  // own rows of V_0: written by this very thread in the prologue
-#pragma unroll
-          for (int ch = 0; ch < CT; ++ch) R[ch] = ldcg4_v(st0 + q * blk + ch * J + j);
-        }
-
         // take the W registers of sequence position idx and refill the slot PFW taps ahead
         auto take_w = [&](auto I) -> float4 {
           constexpr int idx = decltype(I)::value;
@@ -282,7 +300,7 @@ __global__ void __launch_bounds__(kNWF * 32, 2) psf_chain2_fwd_kernel(const Chai
             const int lqp = (lq + ((q + x) >> LOGQ)) & (NQ - 1);
             const float* src = prev + qp * blk + 4 * lqp;
 #pragma unroll
-            for (int ch = 0; ch < CT; ++ch) R[ch] = ldcg4_v(src + ch * J);
+            for (int ch = 0; ch < CT; ++ch) R[ch] = (kAbl & 16) ? make_float4(1.f, 2.f, 3.f, 4.f) : ldcg4_v(src + ch * J);
           }
         };
 
@@ -301,16 +319,23 @@ __global__ void __launch_bounds__(kNWF * 32, 2) psf_chain2_fwd_kernel(const Chai
 #pragma unroll
             for (int ch = 0; ch < CT; ++ch) fma4(acc[ch], w, v[ch]);
           });
-          if constexpr (g == 0) {
-            if (p.residual) {
+          auto issue_tail = [&]() {  // own rows of V_0 (residual): written by this very thread in the prologue
+            if (p.residual && !(kAbl & 4)) {
 #pragma unroll
-              for (int ch = 0; ch < CT; ++ch) add4(acc[ch], R[ch]);
+              for (int ch = 0; ch < CT; ++ch) R[ch] = ldcg4_v(st0 + q * blk + ch * J + j);
             }
-            if (Q > 1 && cw_pending) {  // siblings have published V_{m-1}
+          };
+          if constexpr (g == 0) {
+            if (Q > 1 && cw_pending && !(kAbl & 64)) {  // siblings have published V_{m-1}
               cluster_wait();
               cw_pending = false;
             }
             issue_R(IC<0>{});
+          } else if constexpr (g == G::NR + 1) {
+            if (p.residual) {
+#pragma unroll
+              for (int ch = 0; ch < CT; ++ch) add4(acc[ch], R[ch]);
+            }
           } else if constexpr (g == 1) {
             // ---- head: offsets 0, 1, 2 and tap 3 share the quads A = own rows, Rq = next quad ----
             const float4 w0 = take_w(IC<G::idx_of(0)>{});
@@ -332,19 +357,20 @@ __global__ void __launch_bounds__(kNWF * 32, 2) psf_chain2_fwd_kernel(const Chai
               acc[ch].z = fmaf(w1.z, A.w, acc[ch].z);
               acc[ch].w = fmaf(w1.w, Rq.x, acc[ch].w);
             }
-            if constexpr (1 < G::NR) issue_R(IC<1>{});
+            if constexpr (1 < G::NR) issue_R(IC<1>{}); else issue_tail();
           } else {
             constexpr int r = g - 1;
             const float4 w = take_w(IC<G::idx_of(3 + r)>{});
 #pragma unroll
             for (int ch = 0; ch < CT; ++ch) fma4(acc[ch], w, R[ch]);
-            if constexpr (g < G::NR) issue_R(IC<g>{});
+            if constexpr (g < G::NR) issue_R(IC<g>{}); else issue_tail();
           }
         });
 
         if (!last) {
 #pragma unroll
-          for (int ch = 0; ch < CT; ++ch) st_cg4(next + q * blk + ch * J + j, acc[ch]);
+          for (int ch = 0; ch < CT; ++ch)
+            if (!(kAbl & 32) || acc[ch].x == 123.456f) st_cg4(next + q * blk + ch * J + j, acc[ch]);
         } else {
           store_rows_natural(p.Vout + ((long long)b * n + 4 * (lq * Q + q)) * CT, acc);
         }
@@ -353,7 +379,7 @@ __global__ void __launch_bounds__(kNWF * 32, 2) psf_chain2_fwd_kernel(const Chai
         fence_proxy_async();
         __syncthreads();  // all reads of the shared block and all writes of V_m are done
         if (threadIdx.x == 0) refresh_block<J>(state_u32, vbar, next + q * blk);
-        if (Q > 1) {
+        if (Q > 1 && !(kAbl & 64)) {
           cluster_arrive();  // V_m visible cluster-wide once the (deferred) wait returns
           cw_pending = true;
         }
@@ -368,10 +394,10 @@ __global__ void __launch_bounds__(kNWF * 32, 2) psf_chain2_fwd_kernel(const Chai
 // one shifted read of G feeds both; V_{m-1}[j,:] (saved by the forward pass) sits in registers.
 // ---------------------------------------------------------------------------------------------
 template <int LOGJ, int LOGQ>
-__global__ void __launch_bounds__(kNWB * 32, 2) psf_chain2_bwd_kernel(const Chain2Params p) {
+__global__ void __launch_bounds__(kNWB * 32, PSF2_MINB_BWD) psf_chain2_bwd_kernel(const Chain2Params p) {
   using G = Geo<LOGJ, LOGQ, true>;
   constexpr int J = G::J, Q = G::Q, NQ = G::NQ, kNW = G::NW;
-  constexpr int PFW = 3;
+  constexpr int PFW = PSF2_PFW_BWD;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* state = reinterpret_cast<float*>(smem_raw);
   const uint32_t state_u32 = smem_u32(state);
@@ -394,6 +420,7 @@ __global__ void __launch_bounds__(kNWB * 32, 2) psf_chain2_bwd_kernel(const Chai
   bool cw_pending = false;
 
   // exchange / residual buffers are per CLUSTER (reused sample after sample) so that they stay in L2
+  const unsigned long long keep = make_evict_last_policy();
   float* gx0 = p.gx + (long long)cid * plane;
   float* gx1 = p.gx + ((long long)ncl + cid) * plane;
   float* racc = p.racc + (long long)cid * plane + q * blk;
@@ -409,12 +436,12 @@ __global__ void __launch_bounds__(kNWB * 32, 2) psf_chain2_bwd_kernel(const Chai
       float4 pl[CT];
       load_rows_natural(p.Vin + ((long long)b * n + i0) * CT, pl);
 #pragma unroll
-      for (int ch = 0; ch < CT; ++ch) st_cg4(gx0 + q * blk + ch * J + j, pl[ch]);
+      for (int ch = 0; ch < CT; ++ch) stcg4_keep(gx0 + q * blk + ch * J + j, pl[ch], keep);
     }
     fence_proxy_async();
     __syncthreads();
     if (threadIdx.x == 0) refresh_block<J>(state_u32, vbar, gx0 + q * blk);
-    if (Q > 1) {
+    if (Q > 1 && !(kAbl & 64)) {
       cluster_arrive();
       cw_pending = true;
     }
@@ -455,44 +482,6 @@ __global__ void __launch_bounds__(kNWB * 32, 2) psf_chain2_bwd_kernel(const Chai
           }
         };
 
-        // ---- L2 prefetch: W windows and V_{m-1} rows this warp reads one pass from now ----------
-        if (!(p.dbg & 1)) {
-          int np = pp + 1, nm = m, nb = b;
-          if (np == G::NPASS) {
-            np = 0;
-            if (--nm < 1) {
-              nm = p.n_W;
-              nb = b + ncl;
-            }
-          }
-          if (nb < p.B && np * kNW + warp < G::NT) {
-            const float* nW = p.W + (long long)(nm - 1) * p.sWf + (long long)nb * p.sWb;
-            const int j0 = (np * kNW + warp) * kTileRows;
-            // items: (tap k, line 0..4); taps 1,2 additionally need the window of tap 3 (previous quad)
-            for (int it = lane; it < (G::L + 2) * 5; it += 32) {
-              int k = it / 5;
-              const int line = it - k * 5;
-              int kk = k;  // geometry of the window
-              if (k >= G::L) {
-                kk = 3;
-                k = k - G::L + 1;
-              }
-              int bq = q, shift = 0;
-              if (kk >= 3 && kk < 3 + G::NREM) {
-                const int x = 1 << (kk - 3);
-                bq = (q - x) & (Q - 1);
-                shift = (q < x) ? 4 : 0;
-              } else if (kk >= 3) {
-                shift = 4 << (kk - 3 - G::NREM);
-              }
-              const int start = ((j0 - shift) & (J - 1)) & ~31;
-              prefetch_l2(nW + (long long)k * p.sWt + bq * J + ((start + 32 * line) & (J - 1)));
-            }
-            const float* nV = p.states + ((long long)(nm - 1) * p.B + nb) * plane + q * blk + j0;
-            prefetch_l2(nV + (lane >> 2) * J + (lane & 3) * 32);
-          }
-        }
-
         float4 acc[CT];
         float4 vown[CT];
         float4 R[CT];
@@ -500,7 +489,8 @@ __global__ void __launch_bounds__(kNWB * 32, 2) psf_chain2_bwd_kernel(const Chai
 #pragma unroll
         for (int ch = 0; ch < CT; ++ch) acc[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int ch = 0; ch < CT; ++ch) vown[ch] = __ldcs(reinterpret_cast<const float4*>(vprev + ch * J + j));
+        for (int ch = 0; ch < CT; ++ch)
+          vown[ch] = (kAbl & 8) ? make_float4(1.f, 2.f, 3.f, 4.f) : __ldcs(reinterpret_cast<const float4*>(vprev + ch * J + j));
         static_for<0, PFW>([&](auto I) {
           constexpr int i = decltype(I)::value;
           constexpr int k = G::k_at(i);
@@ -529,7 +519,7 @@ __global__ void __launch_bounds__(kNWB * 32, 2) psf_chain2_bwd_kernel(const Chai
             const int lqp = (lq - (q < x ? 1 : 0)) & (NQ - 1);
             const float* src = gcur + qp * blk + 4 * lqp;
 #pragma unroll
-            for (int ch = 0; ch < CT; ++ch) R[ch] = ldcg4_v(src + ch * J);
+            for (int ch = 0; ch < CT; ++ch) R[ch] = (kAbl & 16) ? make_float4(1.f, 2.f, 3.f, 4.f) : ldcg4_keep(src + ch * J, keep);
           }
           if constexpr (r == 0) {
             w1a = ldg_w4(Wmb + p.sWt + pos_own);
@@ -546,7 +536,8 @@ __global__ void __launch_bounds__(kNWB * 32, 2) psf_chain2_bwd_kernel(const Chai
             fma4(acc[ch], w, g[ch]);
             fma4(dw, g[ch], vown[ch]);
           }
-          st_cs4(dWmb + (long long)k * p.sWt + pos, dw);
+          if constexpr (!(kAbl & 2)) st_cs4(dWmb + (long long)k * p.sWt + pos, dw);
+          else if (dw.x == 123.456f) st_cs4(dWmb, dw);
         };
 
         static_for<0, G::NGRP>([&](auto Gi) {
@@ -562,12 +553,32 @@ __global__ void __launch_bounds__(kNWB * 32, 2) psf_chain2_bwd_kernel(const Chai
             for (int ch = 0; ch < CT; ++ch) v[ch] = lds4(state + ch * J + js);
             tap(v, w, k, q * J + js);
           });
+          auto issue_tail = [&]() {  // running sum of G_m over the factors (residual): this thread's own rows
+            if (p.residual && !first && !(kAbl & 4)) {
+#pragma unroll
+              for (int ch = 0; ch < CT; ++ch) R[ch] = ldcg4_keep(racc + ch * J + j, keep);
+            }
+          };
           if constexpr (g == 0) {
-            if (Q > 1 && cw_pending) {
+            if (Q > 1 && cw_pending && !(kAbl & 64)) {
               cluster_wait();
               cw_pending = false;
             }
             issue_R(IC<0>{});
+          } else if constexpr (g == G::NR + 1) {
+            // residual: dV0 also receives G_m of every factor (V_m = W_m V_{m-1} + V_0)
+            if (p.residual) {
+#pragma unroll
+              for (int ch = 0; ch < CT; ++ch) {
+                float4 own = lds4(state + ch * J + j);
+                if (!first) add4(own, R[ch]);
+                if (!last && !(kAbl & 4)) {
+                  stcg4_keep(racc + ch * J + j, own, keep);
+                } else {
+                  add4(acc[ch], own);
+                }
+              }
+            }
           } else if constexpr (g == 1) {
             // ---- head: tap 3 on the previous quad Rq, then taps 0, 1, 2 on (Rq, own quad A) ----
             const float4 w3 = take_w(IC<G::idx_of(3)>{});
@@ -593,6 +604,9 @@ __global__ void __launch_bounds__(kNWB * 32, 2) psf_chain2_bwd_kernel(const Chai
               fma4(dw2, g2, vown[ch]);
             }
             float* d0 = dWmb + pos_own;
+            if constexpr (kAbl & 2) {
+              if (dw0.x + dw1.x + dw2.x == 123.456f) st_cs4(d0, dw0);
+            } else {
             st_cs4(d0, dw0);
             float* d1 = dWmb + p.sWt;
             __stcs(d1 + pos_r0 + 3, dw1.x);
@@ -601,31 +615,20 @@ __global__ void __launch_bounds__(kNWB * 32, 2) psf_chain2_bwd_kernel(const Chai
             float* d2 = dWmb + 2 * p.sWt;
             st_cs2(d2 + pos_r0 + 2, dw2.x, dw2.y);
             st_cs2(d2 + pos_own, dw2.z, dw2.w);
-            if constexpr (1 < G::NR) issue_R(IC<1>{});
+            }
+            if constexpr (1 < G::NR) issue_R(IC<1>{}); else issue_tail();
           } else {
             constexpr int r = g - 1;
             const float4 w = take_w(IC<G::idx_of(3 + r)>{});
             tap(R, w, 3 + r, wpos(IC<3 + r>{}));
-            if constexpr (g < G::NR) issue_R(IC<g>{});
+            if constexpr (g < G::NR) issue_R(IC<g>{}); else issue_tail();
           }
         });
 
-        // residual: dV0 also receives G_m of every factor (V_m = W_m V_{m-1} + V_0)
-        if (p.residual) {
-#pragma unroll
-          for (int ch = 0; ch < CT; ++ch) {
-            float4 own = lds4(state + ch * J + j);
-            if (!first) add4(own, ldcg4_v(racc + ch * J + j));
-            if (!last) {
-              st_cg4(racc + ch * J + j, own);
-            } else {
-              add4(acc[ch], own);
-            }
-          }
-        }
         if (!last) {
 #pragma unroll
-          for (int ch = 0; ch < CT; ++ch) st_cg4(gnext + q * blk + ch * J + j, acc[ch]);
+          for (int ch = 0; ch < CT; ++ch)
+            if (!(kAbl & 32) || acc[ch].x == 123.456f) stcg4_keep(gnext + q * blk + ch * J + j, acc[ch], keep);
         } else {
           store_rows_natural(p.Vout + ((long long)b * n + 4 * (lq * Q + q)) * CT, acc);
         }
@@ -634,7 +637,7 @@ __global__ void __launch_bounds__(kNWB * 32, 2) psf_chain2_bwd_kernel(const Chai
         fence_proxy_async();
         __syncthreads();
         if (threadIdx.x == 0) refresh_block<J>(state_u32, vbar, gnext + q * blk);
-        if (Q > 1) {
+        if (Q > 1 && !(kAbl & 64)) {
           cluster_arrive();
           cw_pending = true;
         }
@@ -642,7 +645,7 @@ __global__ void __launch_bounds__(kNWB * 32, 2) psf_chain2_bwd_kernel(const Chai
     }
     // the exchange buffers belong to the cluster: the next sample may overwrite them only after every
     // CTA has finished reading this sample's last state
-    if (Q > 1) {
+    if (Q > 1 && !(kAbl & 64)) {
       cluster_arrive();
       cluster_wait();
     }
