@@ -145,6 +145,22 @@ int psf_chain_preferred_interleave(const psf_chain_desc* d);
  * clusters), 1 (contiguous row blocks) or 0 (per-factor path). */
 int psf_chain_fused_generation(const psf_chain_desc* d);
 
+/* ---- the W generators (fs[m] = Linear(E,H) -> GELU -> Linear(H,L), psf.py:110-126, called at :175) ------
+ * All n_W generators in one kernel each way, fp32 FMA.  Supported: E = H = 32, L <= 16 (else
+ * PSF_ERR_UNSUPPORTED and the caller keeps its own GEMM path).
+ *   x [rows,32] row-major; W1 [n_W,32,32] (out,in), b1 [n_W,32], W2 [n_W,L,32], b2 [n_W,L]  (nn.Linear layout)
+ *   W_out / dW_in: element (m, l, row) at m*stride_factor + l*stride_tap + row  (the chain's tap-major layout;
+ *   the row order is that of x).  Backward recomputes the hidden activations and needs
+ *   psf_generators_workspace_bytes(n_W) bytes of device workspace (overwritten). */
+size_t psf_generators_workspace_bytes(int n_W);
+int psf_generators_fwd(const float* x, const float* W1, const float* b1, const float* W2, const float* b2,
+                       float* W_out, int64_t rows, int n_W, int E, int H, int L, int64_t stride_factor,
+                       int64_t stride_tap, psf_stream_t stream);
+int psf_generators_bwd(const float* x, const float* W1, const float* b1, const float* W2, const float* b2,
+                       const float* dW_in, float* dx, float* dW1, float* db1, float* dW2, float* db2,
+                       void* workspace, size_t workspace_bytes, int64_t rows, int n_W, int E, int H, int L,
+                       int64_t stride_factor, int64_t stride_tap, psf_stream_t stream);
+
 /* Launch geometry the fused path would use for this problem (for benches / docs):
  * cluster size, rows per CTA, threads per CTA, dynamic SMEM bytes, resident clusters.
  * Returns PSF_ERR_UNSUPPORTED when the fused path does not cover the shape. */

@@ -54,6 +54,11 @@ _SIGNATURES = {
                                     C.c_int64, C.c_int64, C.c_int, C.c_void_p]),
     "psf_chain_preferred_interleave": (C.c_int, [C.POINTER(ChainDesc)]),
     "psf_chain_fused_generation": (C.c_int, [C.POINTER(ChainDesc)]),
+    "psf_generators_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "psf_generators_fwd": (C.c_int, [C.c_void_p] * 6 + [C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
+                                                         C.c_int64, C.c_void_p]),
+    "psf_generators_bwd": (C.c_int, [C.c_void_p] * 12 + [C.c_size_t, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                          C.c_int64, C.c_int64, C.c_void_p]),
     "psf_chain_fused_plan": (C.c_int, [C.POINTER(ChainDesc), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                        C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
 }

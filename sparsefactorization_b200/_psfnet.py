@@ -12,6 +12,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import _capi
+from . import generators as _gen
 from .chain import chord_chain, preferred_interleave, row_permutation
 
 
@@ -147,6 +148,9 @@ class _TapMajorLastLinear(torch.autograd.Function):
         return dh, dw, db
 
 
+USE_FUSED_GENERATORS = True      # tests flip this to compare against the batched-GEMM route
+
+
 def generate_factors(fs: Sequence[MLPBlock], data: torch.Tensor, interleave: int = 1) -> torch.Tensor:
     """``W[m] = fs[m](data)`` for every m (psf.py:175), computed as batched GEMMs.
 
@@ -164,6 +168,9 @@ def generate_factors(fs: Sequence[MLPBlock], data: torch.Tensor, interleave: int
     if interleave > 1:
         data = data.view(B, n // (4 * interleave), interleave, 4, E).permute(0, 2, 1, 3, 4).reshape(B, n, E)
     x_shared = data.reshape(B * n, E)
+    if USE_FUSED_GENERATORS and _gen.fusable(fs, data):
+        wt = _gen.fused_generators(fs, x_shared)                   # [n_W, L, B*n], one kernel
+        return wt.view(n_W, wt.shape[1], B, n).permute(0, 2, 3, 1)
     if not _same_structure(fs):
         # heterogeneous generators: evaluate one by one (reference order), then re-lay
         return torch.stack([f(data) for f in fs], 0)

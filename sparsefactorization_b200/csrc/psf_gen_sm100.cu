@@ -1,0 +1,512 @@
+// Fused W generators for sm_100a: every fs[m] = Linear(E,H) -> GELU -> Linear(H,L) of PSFNet
+// (SyntheticExperiments/psf.py:110-126, evaluated at psf.py:175) in ONE kernel each way, fp32 FMA only
+// (no TF32: the chain's parity tolerance is rtol 1e-5), E = H = 32, L <= 16.
+//
+//   forward : x [rows, 32] -> W [n_W][L][rows]  (tap-major: the chain's streaming layout; `rows` = B*n in
+//             whatever row order x is given in, so a quad-interleaved x yields a quad-interleaved W)
+//             thread = one row: x stays in registers for all n_W generators, weights are broadcast
+//             reads from shared memory, hidden activations never leave registers.  HBM traffic is the
+//             compulsory 128 B in + 4*L*n_W B out per row (the cuBLAS route wrote and re-read three
+//             [rows, n_W*32] buffers).
+//   backward: dW [n_W][L][rows] -> dx [rows,32], dW1, db1, dW2, db2.  The hidden activations are
+//             RECOMPUTED from x (1 KFMA per row and generator; saving them would be 3.9 GB at the
+//             headline shape).  Per 256-row tile and generator:
+//               phase 1 (thread = row): pre, gelu, gelu', dhid = dout W2, dpre, dx += dpre W1;
+//                        dpre / hid / dout staged in shared memory,
+//               phase 2 (thread = 8x8 output tile x one row group): dW1 += dpre^T x, dW2 += dout^T hid
+//                        as register-tiled outer products over the tile's rows, reduced across row
+//                        groups with a shuffle reduce-scatter, accumulated into a per-CTA slice of a
+//                        global workspace (plain read-modify-write by the owning thread: deterministic).
+//             A second tiny kernel sums the per-CTA slices in a fixed order.
+#include "psf_internal.cuh"
+
+namespace {
+
+constexpr int GE = 32;    // embedding width
+constexpr int GH = 32;    // hidden width
+constexpr int GLP = 16;   // taps padded
+constexpr int kBlkFwd = GH * GE + GH + GH * GLP + GLP;  // w1[h][e], b1[h], w2t[h][l], b2[l]  = 1584 floats
+constexpr int kBlkBwd = GH * GE + GH + GLP * GH;        // w1[h][e], b1[h], w2[l][h]          = 1568 floats
+constexpr int kAccBlk = GH * GE + GH + GLP * GH + GLP;  // dW1, db1, dW2 (l-major, padded), db2 = 1584 floats
+constexpr int kTile = 256;                               // rows per tile == threads per CTA
+constexpr int XS = GE + 4;                               // padded row stride of the staged tiles (bank-conflict free)
+constexpr int DS = GLP + 4;
+
+__device__ __forceinline__ void ffma2(float2& c, const float2& a, const float2& b) {
+  unsigned long long* pc = reinterpret_cast<unsigned long long*>(&c);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;"
+      : "+l"(*pc)
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+}
+__device__ __forceinline__ float4 lds4g(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// exact GELU as ATen evaluates it in fp32: x * 0.5 * (1 + erf(x / sqrt 2))
+__device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f)); }
+
+struct GenParams {
+  const float* x;
+  const float* W1;  // [n_W][32][32]
+  const float* b1;  // [n_W][32]
+  const float* W2;  // [n_W][L][32]
+  const float* b2;  // [n_W][L]
+  float* Wt;        // fwd: out [n_W][L][rows];  bwd: dW (same layout, read)
+  float* dx;        // bwd: [rows][32]
+  float* ws;        // bwd: [grid][n_W][kAccBlk]
+  long long rows, sWf, sWt;
+  int n_W, L;
+};
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTile, 2) psf_gen_fwd_kernel(const GenParams p) {
+  extern __shared__ __align__(16) float gsm[];
+  // all generators' weights -> shared memory, once per (persistent) CTA
+  for (int idx = threadIdx.x; idx < p.n_W * kBlkFwd; idx += kTile) {
+    const int m = idx / kBlkFwd;
+    int o = idx - m * kBlkFwd;
+    float v;
+    if (o < GH * GE) {
+      v = p.W1[(long long)m * GH * GE + o];
+    } else if ((o -= GH * GE) < GH) {
+      v = p.b1[m * GH + o];
+    } else if ((o -= GH) < GH * GLP) {
+      const int h = o / GLP, l = o - h * GLP;
+      v = l < p.L ? p.W2[((long long)m * p.L + l) * GH + h] : 0.f;
+    } else {
+      o -= GH * GLP;
+      v = o < p.L ? p.b2[m * p.L + o] : 0.f;
+    }
+    gsm[idx] = v;
+  }
+  __syncthreads();
+
+  const long long ntiles = (p.rows + kTile - 1) / kTile;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row = tile * kTile + threadIdx.x;
+    if (row >= p.rows) continue;
+    float2 x2[GE / 2];
+    {
+      const float4* xr = reinterpret_cast<const float4*>(p.x + row * GE);
+#pragma unroll
+      for (int i = 0; i < GE / 4; ++i) {
+        const float4 v = __ldg(xr + i);
+        x2[2 * i] = make_float2(v.x, v.y);
+        x2[2 * i + 1] = make_float2(v.z, v.w);
+      }
+    }
+#pragma unroll 1
+    for (int m = 0; m < p.n_W; ++m) {
+      const float* w1 = gsm + m * kBlkFwd;
+      const float* b1 = w1 + GH * GE;
+      const float* w2t = b1 + GH;
+      const float* b2 = w2t + GH * GLP;
+      float2 out2[GLP / 2];
+#pragma unroll
+      for (int i = 0; i < GLP / 4; ++i) {
+        const float4 b = lds4g(b2 + 4 * i);
+        out2[2 * i] = make_float2(b.x, b.y);
+        out2[2 * i + 1] = make_float2(b.z, b.w);
+      }
+#pragma unroll
+      for (int hc = 0; hc < GH / 8; ++hc) {
+        float2 pre2[8];
+#pragma unroll
+        for (int h = 0; h < 8; ++h) pre2[h] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int e4 = 0; e4 < GE / 4; ++e4) {
+#pragma unroll
+          for (int h = 0; h < 8; ++h) {
+            const float4 w = lds4g(w1 + (hc * 8 + h) * GE + 4 * e4);
+            ffma2(pre2[h], make_float2(w.x, w.y), x2[2 * e4]);
+            ffma2(pre2[h], make_float2(w.z, w.w), x2[2 * e4 + 1]);
+          }
+        }
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+          const float hid = gelu_f(pre2[h].x + pre2[h].y + b1[hc * 8 + h]);
+          const float2 hh = make_float2(hid, hid);
+#pragma unroll
+          for (int l4 = 0; l4 < GLP / 4; ++l4) {
+            const float4 w = lds4g(w2t + (hc * 8 + h) * GLP + 4 * l4);
+            ffma2(out2[2 * l4], make_float2(w.x, w.y), hh);
+            ffma2(out2[2 * l4 + 1], make_float2(w.z, w.w), hh);
+          }
+        }
+      }
+      float* dst = p.Wt + (long long)m * p.sWf + row;
+#pragma unroll
+      for (int l = 0; l < GLP; ++l)
+        if (l < p.L) dst[(long long)l * p.sWt] = (l & 1) ? out2[l >> 1].y : out2[l >> 1].x;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+// reduce-scatter step over lane bit M of N+N values: afterwards v[0..N) holds the pairwise sums of the half
+// this lane keeps (lanes with the bit clear keep the first half)
+template <int N>
+__device__ __forceinline__ void rs_step2(float2* v, int M, bool hi) {  // same on N+N float2 values
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const float2 send = hi ? v[i] : v[i + N];
+    const float2 keep = hi ? v[i + N] : v[i];
+    v[i].x = keep.x + __shfl_xor_sync(0xffffffffu, send.x, M);
+    v[i].y = keep.y + __shfl_xor_sync(0xffffffffu, send.y, M);
+  }
+}
+template <int N>
+__device__ __forceinline__ void rs_step(float* v, int M, bool hi) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const float send = hi ? v[i] : v[i + N];
+    const float keep = hi ? v[i + N] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, M);
+  }
+}
+
+__global__ void __launch_bounds__(kTile, 1) psf_gen_bwd_kernel(const GenParams p) {
+  extern __shared__ __align__(16) float gsm[];
+  float* xs = gsm;                    // [kTile][XS]   x rows of the tile
+  float* dps = xs + kTile * XS;       // [kTile][XS]   dpre
+  float* hs = dps + kTile * XS;       // [kTile][XS]   hidden activations
+  float* dos = hs + kTile * XS;       // [kTile][DS]   dout (taps padded with zeros)
+  float* wb = dos + kTile * DS;       // weights of the current generator
+  const float* w1 = wb;
+  const float* b1 = wb + GH * GE;
+  const float* w2 = b1 + GH;          // [GLP][GH], rows >= L are zero
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* wsc = p.ws + (long long)blockIdx.x * p.n_W * kAccBlk;
+  const long long ntiles = (p.rows + kTile - 1) / kTile;
+
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row = tile * kTile + tid;
+    const bool live = row < p.rows;
+    float2 x2[GE / 2], dx2[GE / 2];
+#pragma unroll
+    for (int i = 0; i < GE / 4; ++i) {
+      const float4 v = live ? __ldg(reinterpret_cast<const float4*>(p.x + row * GE) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      x2[2 * i] = make_float2(v.x, v.y);
+      x2[2 * i + 1] = make_float2(v.z, v.w);
+      dx2[2 * i] = make_float2(0.f, 0.f);
+      dx2[2 * i + 1] = make_float2(0.f, 0.f);
+    }
+    __syncthreads();  // phase 2 of the previous tile has finished reading xs
+#pragma unroll
+    for (int i = 0; i < GE / 4; ++i)
+      *reinterpret_cast<float4*>(xs + tid * XS + 4 * i) = make_float4(x2[2 * i].x, x2[2 * i].y, x2[2 * i + 1].x, x2[2 * i + 1].y);
+
+#pragma unroll 1
+    for (int m = 0; m < p.n_W; ++m) {
+      __syncthreads();  // phase 2 of the previous generator is done with dps / hs / dos and the weights
+      for (int o = tid; o < kBlkBwd; o += kTile) {
+        float v;
+        if (o < GH * GE) {
+          v = p.W1[(long long)m * GH * GE + o];
+        } else if (o < GH * GE + GH) {
+          v = p.b1[m * GH + (o - GH * GE)];
+        } else {
+          const int q = o - GH * GE - GH, l = q / GH;
+          v = l < p.L ? p.W2[(long long)m * p.L * GH + q] : 0.f;
+        }
+        wb[o] = v;
+      }
+      float dout[GLP];
+      {
+        const float* src = p.Wt + (long long)m * p.sWf + row;
+#pragma unroll
+        for (int l = 0; l < GLP; ++l) dout[l] = (live && l < p.L) ? __ldcs(src + (long long)l * p.sWt) : 0.f;
+#pragma unroll
+        for (int i = 0; i < GLP / 4; ++i)
+          *reinterpret_cast<float4*>(dos + tid * DS + 4 * i) = make_float4(dout[4 * i], dout[4 * i + 1], dout[4 * i + 2], dout[4 * i + 3]);
+      }
+      __syncthreads();
+
+      // ---- phase 1: this thread's row ------------------------------------------------------
+#pragma unroll
+      for (int hc = 0; hc < GH / 8; ++hc) {
+        float2 pre2[8];
+#pragma unroll
+        for (int h = 0; h < 8; ++h) pre2[h] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int e4 = 0; e4 < GE / 4; ++e4) {
+#pragma unroll
+          for (int h = 0; h < 8; ++h) {
+            const float4 w = lds4g(w1 + (hc * 8 + h) * GE + 4 * e4);
+            ffma2(pre2[h], make_float2(w.x, w.y), x2[2 * e4]);
+            ffma2(pre2[h], make_float2(w.z, w.w), x2[2 * e4 + 1]);
+          }
+        }
+        float2 dh2[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dh2[i] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int l = 0; l < GLP; ++l) {
+          const float2 dd = make_float2(dout[l], dout[l]);
+          const float4 wa = lds4g(w2 + l * GH + hc * 8);
+          const float4 wc = lds4g(w2 + l * GH + hc * 8 + 4);
+          ffma2(dh2[0], make_float2(wa.x, wa.y), dd);
+          ffma2(dh2[1], make_float2(wa.z, wa.w), dd);
+          ffma2(dh2[2], make_float2(wc.x, wc.y), dd);
+          ffma2(dh2[3], make_float2(wc.z, wc.w), dd);
+        }
+        float hid[8], dpre[8];
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+          const float pre = pre2[h].x + pre2[h].y + b1[hc * 8 + h];
+          const float cdf = 0.5f * (1.f + erff(pre * 0.70710678118654752440f));
+          const float pdf = 0.39894228040143267794f * expf(-0.5f * pre * pre);
+          hid[h] = pre * cdf;
+          const float dhid = (h & 1) ? dh2[h >> 1].y : dh2[h >> 1].x;
+          dpre[h] = dhid * (cdf + pre * pdf);
+        }
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+          const float2 dd = make_float2(dpre[h], dpre[h]);
+#pragma unroll
+          for (int e4 = 0; e4 < GE / 4; ++e4) {
+            const float4 w = lds4g(w1 + (hc * 8 + h) * GE + 4 * e4);
+            ffma2(dx2[2 * e4], make_float2(w.x, w.y), dd);
+            ffma2(dx2[2 * e4 + 1], make_float2(w.z, w.w), dd);
+          }
+        }
+        *reinterpret_cast<float4*>(dps + tid * XS + hc * 8) = make_float4(dpre[0], dpre[1], dpre[2], dpre[3]);
+        *reinterpret_cast<float4*>(dps + tid * XS + hc * 8 + 4) = make_float4(dpre[4], dpre[5], dpre[6], dpre[7]);
+        *reinterpret_cast<float4*>(hs + tid * XS + hc * 8) = make_float4(hid[0], hid[1], hid[2], hid[3]);
+        *reinterpret_cast<float4*>(hs + tid * XS + hc * 8 + 4) = make_float4(hid[4], hid[5], hid[6], hid[7]);
+      }
+      __syncthreads();
+
+      float* acc_m = wsc + (long long)m * kAccBlk;
+      // ---- phase 2a: dW1[h][e] += sum_rows dpre[row][h] * x[row][e]  (+ db1) -----------------
+      {
+        const int kg = lane & 15;                                   // row group: rows rr*16 + kg
+        const int hb = warp >> 1, eb = ((warp & 1) << 1) | (lane >> 4);
+        float2 v[32];  // v[i * 4 + j] = outputs (i, 2j), (i, 2j + 1) of the 8 x 8 tile
+        float db[8];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) db[i] = 0.f;
+#pragma unroll 2
+        for (int rr = 0; rr < kTile / 16; ++rr) {
+          const int r = rr * 16 + kg;
+          const float4 d0 = lds4g(dps + r * XS + hb * 8), d1 = lds4g(dps + r * XS + hb * 8 + 4);
+          const float4 a0 = lds4g(xs + r * XS + eb * 8), a1 = lds4g(xs + r * XS + eb * 8 + 4);
+          const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+          const float2 aa[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y),
+                                make_float2(a1.z, a1.w)};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float2 di = make_float2(dd[i], dd[i]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ffma2(v[i * 4 + j], aa[j], di);
+            db[i] += dd[i];
+          }
+        }
+        rs_step2<16>(v, 8, lane & 8);
+        rs_step2<8>(v, 4, lane & 4);
+        rs_step2<4>(v, 2, lane & 2);
+        rs_step2<2>(v, 1, lane & 1);
+        const int o = ((lane & 8) ? 32 : 0) + ((lane & 4) ? 16 : 0) + ((lane & 2) ? 8 : 0) + ((lane & 1) ? 4 : 0);
+        float4* dst = reinterpret_cast<float4*>(acc_m + (hb * 8 + (o >> 3)) * GE + eb * 8 + (o & 7));
+        float4 cur = *dst;
+        cur.x += v[0].x;
+        cur.y += v[0].y;
+        cur.z += v[1].x;
+        cur.w += v[1].y;
+        *dst = cur;
+        // bias gradient: the eb == 0 half-warps hold the column sums of dpre
+        rs_step<4>(db, 8, lane & 8);
+        rs_step<2>(db, 4, lane & 4);
+        rs_step<1>(db, 2, lane & 2);
+        db[0] += __shfl_xor_sync(0xffffffffu, db[0], 1);
+        if (eb == 0 && !(lane & 1)) {
+          const int h = hb * 8 + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
+          acc_m[GH * GE + h] += db[0];
+        }
+      }
+      // ---- phase 2b: dW2[l][h] += sum_rows dout[row][l] * hid[row][h]  (+ db2) ----------------
+      {
+        const int kg = lane;                                        // row group: rows rr*32 + kg
+        const int lb = warp >> 2, hb = warp & 3;
+        float2 v[32];  // v[i * 4 + j] = outputs (i, 2j), (i, 2j + 1) of the 8 x 8 tile
+        float db[8];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) db[i] = 0.f;
+#pragma unroll 2
+        for (int rr = 0; rr < kTile / 32; ++rr) {
+          const int r = rr * 32 + kg;
+          const float4 d0 = lds4g(dos + r * DS + lb * 8), d1 = lds4g(dos + r * DS + lb * 8 + 4);
+          const float4 a0 = lds4g(hs + r * XS + hb * 8), a1 = lds4g(hs + r * XS + hb * 8 + 4);
+          const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+          const float2 aa[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y),
+                                make_float2(a1.z, a1.w)};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float2 di = make_float2(dd[i], dd[i]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ffma2(v[i * 4 + j], aa[j], di);
+            db[i] += dd[i];
+          }
+        }
+        rs_step2<16>(v, 16, lane & 16);
+        rs_step2<8>(v, 8, lane & 8);
+        rs_step2<4>(v, 4, lane & 4);
+        rs_step2<2>(v, 2, lane & 2);
+        rs_step2<1>(v, 1, lane & 1);
+        const int o = ((lane & 16) ? 32 : 0) + ((lane & 8) ? 16 : 0) + ((lane & 4) ? 8 : 0) + ((lane & 2) ? 4 : 0) +
+                      ((lane & 1) ? 2 : 0);
+        float2* dst = reinterpret_cast<float2*>(acc_m + GH * GE + GH + (lb * 8 + (o >> 3)) * GH + hb * 8 + (o & 7));
+        float2 cur = *dst;
+        cur.x += v[0].x;
+        cur.y += v[0].y;
+        *dst = cur;
+        rs_step<4>(db, 16, lane & 16);
+        rs_step<2>(db, 8, lane & 8);
+        rs_step<1>(db, 4, lane & 4);
+        db[0] += __shfl_xor_sync(0xffffffffu, db[0], 2);
+        db[0] += __shfl_xor_sync(0xffffffffu, db[0], 1);
+        if (hb == 0 && !(lane & 3)) {
+          const int l = lb * 8 + ((lane & 16) ? 4 : 0) + ((lane & 8) ? 2 : 0) + ((lane & 4) ? 1 : 0);
+          acc_m[GH * GE + GH + GLP * GH + l] += db[0];
+        }
+      }
+    }
+    if (live) {
+      float4* dst = reinterpret_cast<float4*>(p.dx + row * GE);
+#pragma unroll
+      for (int i = 0; i < GE / 4; ++i) dst[i] = make_float4(dx2[2 * i].x, dx2[2 * i].y, dx2[2 * i + 1].x, dx2[2 * i + 1].y);
+    }
+  }
+}
+
+// sum the per-CTA slices in a fixed order and scatter into the parameter-gradient tensors
+__global__ void psf_gen_reduce_kernel(const float* __restrict__ ws, int nslices, int n_W, int L, float* __restrict__ dW1,
+                                      float* __restrict__ db1, float* __restrict__ dW2, float* __restrict__ db2) {
+  const int total = n_W * kAccBlk;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int c = 0; c < nslices; ++c) s += ws[(long long)c * total + idx];
+    const int m = idx / kAccBlk;
+    int o = idx - m * kAccBlk;
+    if (o < GH * GE) {
+      dW1[(long long)m * GH * GE + o] = s;
+    } else if ((o -= GH * GE) < GH) {
+      db1[m * GH + o] = s;
+    } else if ((o -= GH) < GLP * GH) {
+      const int l = o / GH;
+      if (l < L) dW2[((long long)m * L + l) * GH + (o - l * GH)] = s;
+    } else {
+      o -= GLP * GH;
+      if (o < L) db2[m * L + o] = s;
+    }
+  }
+}
+
+bool g_gen_attr = false;
+
+int gen_grid(int per_sm) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms * per_sm;
+}
+
+constexpr int kSmemBwd = (3 * kTile * XS + kTile * DS + kBlkBwd) * 4;
+
+int gen_check(int64_t rows, int n_W, int E, int H, int L) {
+  if (E != GE || H != GH || L < 1 || L > GLP || n_W < 1 || rows < 1) return PSF_ERR_UNSUPPORTED;
+  if (n_W * kBlkFwd * 4 > 110 * 1024) return PSF_ERR_UNSUPPORTED;  // forward keeps every generator's weights resident
+  if (!g_gen_attr) {
+    if (cudaFuncSetAttribute(psf_gen_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(psf_gen_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBwd) != cudaSuccess) {
+      cudaGetLastError();
+      return PSF_ERR_UNSUPPORTED;
+    }
+    g_gen_attr = true;
+  }
+  return PSF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t psf_generators_workspace_bytes(int n_W) {
+  if (n_W < 1) return 0;
+  return psf_round256((size_t)gen_grid(1) * (size_t)n_W * kAccBlk * sizeof(float));
+}
+
+int psf_generators_fwd(const float* x, const float* W1, const float* b1, const float* W2, const float* b2, float* W_out,
+                       int64_t rows, int n_W, int E, int H, int L, int64_t stride_factor, int64_t stride_tap,
+                       psf_stream_t stream) {
+  if (x == nullptr || W1 == nullptr || b1 == nullptr || W2 == nullptr || b2 == nullptr || W_out == nullptr) return PSF_ERR_ARG;
+  if (rows == 0) return PSF_OK;
+  int rc = gen_check(rows, n_W, E, H, L);
+  if (rc) return rc;
+  if (reinterpret_cast<uintptr_t>(x) & 15) return PSF_ERR_ARG;
+  GenParams p = {};
+  p.x = x;
+  p.W1 = W1;
+  p.b1 = b1;
+  p.W2 = W2;
+  p.b2 = b2;
+  p.Wt = W_out;
+  p.rows = rows;
+  p.sWf = stride_factor;
+  p.sWt = stride_tap;
+  p.n_W = n_W;
+  p.L = L;
+  const long long ntiles = (rows + kTile - 1) / kTile;
+  long long grid = gen_grid(2);
+  if (grid > ntiles) grid = ntiles;
+  psf_gen_fwd_kernel<<<(unsigned)grid, kTile, (size_t)n_W * kBlkFwd * 4, (cudaStream_t)stream>>>(p);
+  return (int)cudaGetLastError();
+}
+
+int psf_generators_bwd(const float* x, const float* W1, const float* b1, const float* W2, const float* b2,
+                       const float* dW_in, float* dx, float* dW1, float* db1, float* dW2, float* db2, void* workspace,
+                       size_t workspace_bytes, int64_t rows, int n_W, int E, int H, int L, int64_t stride_factor,
+                       int64_t stride_tap, psf_stream_t stream) {
+  if (x == nullptr || W1 == nullptr || b1 == nullptr || W2 == nullptr || b2 == nullptr || dW_in == nullptr ||
+      dx == nullptr || dW1 == nullptr || db1 == nullptr || dW2 == nullptr || db2 == nullptr)
+    return PSF_ERR_ARG;
+  int rc = gen_check(rows < 1 ? 1 : rows, n_W, E, H, L);
+  if (rc) return rc;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(dx) & 15)) return PSF_ERR_ARG;
+  if (workspace == nullptr || workspace_bytes < psf_generators_workspace_bytes(n_W)) return PSF_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long ntiles = (rows + kTile - 1) / kTile;
+  long long grid = gen_grid(1);
+  if (grid > ntiles) grid = ntiles;
+  if (grid < 1) grid = 1;
+  PSF_CUDA_TRY(cudaMemsetAsync(workspace, 0, (size_t)grid * n_W * kAccBlk * sizeof(float), st));
+  GenParams p = {};
+  p.x = x;
+  p.W1 = W1;
+  p.b1 = b1;
+  p.W2 = W2;
+  p.b2 = b2;
+  p.Wt = const_cast<float*>(dW_in);
+  p.dx = dx;
+  p.ws = (float*)workspace;
+  p.rows = rows;
+  p.sWf = stride_factor;
+  p.sWt = stride_tap;
+  p.n_W = n_W;
+  p.L = L;
+  if (rows > 0) {
+    psf_gen_bwd_kernel<<<(unsigned)grid, kTile, kSmemBwd, st>>>(p);
+    PSF_CUDA_TRY(cudaGetLastError());
+  }
+  psf_gen_reduce_kernel<<<(n_W * kAccBlk + 255) / 256, 256, 0, st>>>((const float*)workspace, (int)grid, n_W, L, dW1, db1,
+                                                                    dW2, db2);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -101,3 +101,80 @@ def test_train_model_loop_learns_adding_small():
                       "adding", saving_criteria=1000.0)
     assert len(hist) == 3 and hist[-1]["train_loss"] < hist[0]["train_loss"]
     assert np.isfinite(hist[-1]["test_loss"])
+
+
+@pytest.mark.parametrize("B,n,n_W,L", [(3, 256, 5, 15), (1, 100, 3, 9), (2, 1000, 2, 16), (2, 4096, 12, 13)])
+def test_fused_generators_match_modules_forward_and_backward(B, n, n_W, L):
+    """psf_generators_fwd/bwd (one kernel each way, hidden activations recomputed) against the per-module
+    torch evaluation fs[m](data) of the reference (psf.py:175) in fp64, and against the fp32 torch route."""
+    from sparsefactorization_b200 import _psfnet, generators
+    from sparsefactorization_b200._psfnet import MLPBlock, generate_factors
+    torch.manual_seed(n + L)
+    fs = torch.nn.ModuleList([MLPBlock([32, "GELU"], 32, L) for _ in range(n_W)]).cuda()
+    data = torch.randn(B, n, 32, device="cuda", requires_grad=True)
+    gW = torch.randn(n_W, B, n, L, device="cuda") / n
+    assert generators.fusable(fs, data)
+
+    def run(fused):
+        _psfnet.USE_FUSED_GENERATORS = fused
+        try:
+            for p in fs.parameters():
+                p.grad = None
+            data.grad = None
+            before = generators.stats.launches
+            W = generate_factors(fs, data)
+            assert (generators.stats.launches > before) == fused
+            assert W.shape == (n_W, B, n, L) and W.stride(2) == 1
+            W.backward(gW)
+            return W.detach().clone(), data.grad.clone(), [p.grad.clone() for p in fs.parameters()]
+        finally:
+            _psfnet.USE_FUSED_GENERATORS = True
+
+    W1, dx1, g1 = run(True)
+    W0, dx0, g0 = run(False)
+    # fp64 ground truth from the modules themselves
+    fs64 = torch.nn.ModuleList([MLPBlock([32, "GELU"], 32, L) for _ in range(n_W)]).cuda().double()
+    fs64.load_state_dict({k: v.double() for k, v in fs.state_dict().items()})
+    d64 = data.detach().double().requires_grad_(True)
+    W64 = torch.stack([f(d64) for f in fs64], 0)
+    W64.backward(gW.double())
+    g64 = [p.grad for p in fs64.parameters()]
+
+    def check(got, ref32, ref64, what):
+        err = (got.double() - ref64).abs().max().item()
+        err32 = (ref32.double() - ref64).abs().max().item()
+        scale = ref64.abs().max().item()
+        assert err <= 4 * err32 + 2e-6 * scale + 1e-9, f"{what}: ours {err:.3e} vs torch-fp32 {err32:.3e} (scale {scale:.3e})"
+
+    check(W1, W0, W64.detach(), "W")
+    torch.testing.assert_close(W1, W64.float(), rtol=1e-5, atol=1e-6)
+    check(dx1, dx0, d64.grad, "d data")
+    for a, b, c, (name, _) in zip(g1, g0, g64, fs.named_parameters()):
+        check(a, b, c, name)
+
+
+def test_fused_generators_full_size_equal_gemm_route():
+    """BASELINE cfg2 shape (n = 16384, 14 generators, 15 taps), batch 8: fused kernels vs the batched-GEMM route."""
+    from sparsefactorization_b200 import _psfnet
+    from sparsefactorization_b200._psfnet import MLPBlock, generate_factors
+    torch.manual_seed(1)
+    B, n, n_W, L = 8, 16384, 14, 15
+    fs = torch.nn.ModuleList([MLPBlock([32, "GELU"], 32, L) for _ in range(n_W)]).cuda()
+    data = torch.randn(B, n, 32, device="cuda", requires_grad=True)
+    gW = torch.randn(n_W, L, B, n, device="cuda").permute(0, 2, 3, 1) / n
+    res = {}
+    for fused in (True, False):
+        _psfnet.USE_FUSED_GENERATORS = fused
+        try:
+            for p in fs.parameters():
+                p.grad = None
+            data.grad = None
+            W = generate_factors(fs, data, interleave=8)
+            W.backward(gW)
+            res[fused] = (W.detach().clone(), data.grad.clone(), [p.grad.clone() for p in fs.parameters()])
+        finally:
+            _psfnet.USE_FUSED_GENERATORS = True
+    torch.testing.assert_close(res[True][0], res[False][0], rtol=1e-5, atol=2e-6)
+    torch.testing.assert_close(res[True][1], res[False][1], rtol=1e-4, atol=1e-7)
+    for a, b in zip(res[True][2], res[False][2]):
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5 * float(b.abs().max()))
