@@ -10,7 +10,8 @@
 //             [rows, n_W*32] buffers).
 //   backward: dW [n_W][L][rows] -> dx [rows,32], dW1, db1, dW2, db2.  The hidden activations are
 //             RECOMPUTED from x (1 KFMA per row and generator; saving them would be 3.9 GB at the
-//             headline shape).  Per 256-row tile and generator:
+//             headline shape).  Per 128-row tile and generator (128 threads, three CTAs per SM so that
+//             the phases of different tiles overlap):
 //               phase 1 (thread = row): pre, gelu, gelu', dhid = dout W2, dpre, dx += dpre W1;
 //                        dpre / hid / dout staged in shared memory,
 //               phase 2 (thread = 8x8 output tile x one row group): dW1 += dpre^T x, dW2 += dout^T hid
@@ -28,7 +29,8 @@ constexpr int GLP = 16;   // taps padded
 constexpr int kBlkFwd = GH * GE + GH + GH * GLP + GLP;  // w1[h][e], b1[h], w2t[h][l], b2[l]  = 1584 floats
 constexpr int kBlkBwd = GH * GE + GH + GLP * GH;        // w1[h][e], b1[h], w2[l][h]          = 1568 floats
 constexpr int kAccBlk = GH * GE + GH + GLP * GH + GLP;  // dW1, db1, dW2 (l-major, padded), db2 = 1584 floats
-constexpr int kTile = 256;                               // rows per tile == threads per CTA
+constexpr int kTile = 256;                               // forward: rows per tile == threads per CTA
+constexpr int kTB = 128;                                 // backward: rows per tile == threads per CTA (3 CTAs per SM)
 constexpr int XS = GE + 4;                               // padded row stride of the staged tiles (bank-conflict free)
 constexpr int DS = GLP + 4;
 
@@ -167,42 +169,40 @@ __device__ __forceinline__ void rs_step(float* v, int M, bool hi) {
   }
 }
 
-__global__ void __launch_bounds__(kTile, 1) psf_gen_bwd_kernel(const GenParams p) {
+__global__ void __launch_bounds__(kTB, 3) psf_gen_bwd_kernel(const GenParams p) {
   extern __shared__ __align__(16) float gsm[];
-  float* xs = gsm;                    // [kTile][XS]   x rows of the tile
-  float* dps = xs + kTile * XS;       // [kTile][XS]   dpre
-  float* hs = dps + kTile * XS;       // [kTile][XS]   hidden activations
-  float* dos = hs + kTile * XS;       // [kTile][DS]   dout (taps padded with zeros)
-  float* wb = dos + kTile * DS;       // weights of the current generator
+  float* xs = gsm;                    // [kTB][XS]   x rows of the tile
+  float* dps = xs + kTB * XS;       // [kTB][XS]   dpre
+  float* hs = dps + kTB * XS;       // [kTB][XS]   hidden activations
+  float* dos = hs + kTB * XS;       // [kTB][DS]   dout (taps padded with zeros)
+  float* wb = dos + kTB * DS;       // weights of the current generator
   const float* w1 = wb;
   const float* b1 = wb + GH * GE;
   const float* w2 = b1 + GH;          // [GLP][GH], rows >= L are zero
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* wsc = p.ws + (long long)blockIdx.x * p.n_W * kAccBlk;
-  const long long ntiles = (p.rows + kTile - 1) / kTile;
+  const long long ntiles = (p.rows + kTB - 1) / kTB;
 
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long row = tile * kTile + tid;
+    const long long row = tile * kTB + tid;
     const bool live = row < p.rows;
-    float2 x2[GE / 2], dx2[GE / 2];
+    float2 dx2[GE / 2];
+    float4 xin[GE / 4];
 #pragma unroll
     for (int i = 0; i < GE / 4; ++i) {
-      const float4 v = live ? __ldg(reinterpret_cast<const float4*>(p.x + row * GE) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-      x2[2 * i] = make_float2(v.x, v.y);
-      x2[2 * i + 1] = make_float2(v.z, v.w);
+      xin[i] = live ? __ldg(reinterpret_cast<const float4*>(p.x + row * GE) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
       dx2[2 * i] = make_float2(0.f, 0.f);
       dx2[2 * i + 1] = make_float2(0.f, 0.f);
     }
     __syncthreads();  // phase 2 of the previous tile has finished reading xs
 #pragma unroll
-    for (int i = 0; i < GE / 4; ++i)
-      *reinterpret_cast<float4*>(xs + tid * XS + 4 * i) = make_float4(x2[2 * i].x, x2[2 * i].y, x2[2 * i + 1].x, x2[2 * i + 1].y);
+    for (int i = 0; i < GE / 4; ++i) *reinterpret_cast<float4*>(xs + tid * XS + 4 * i) = xin[i];
 
 #pragma unroll 1
     for (int m = 0; m < p.n_W; ++m) {
       __syncthreads();  // phase 2 of the previous generator is done with dps / hs / dos and the weights
-      for (int o = tid; o < kBlkBwd; o += kTile) {
+      for (int o = tid; o < kBlkBwd; o += kTB) {
         float v;
         if (o < GH * GE) {
           v = p.W1[(long long)m * GH * GE + o];
@@ -225,8 +225,16 @@ __global__ void __launch_bounds__(kTile, 1) psf_gen_bwd_kernel(const GenParams p
       }
       __syncthreads();
 
-      // ---- phase 1: this thread's row ------------------------------------------------------
+      // ---- phase 1: this thread's row (x comes back from the staged tile: it is not kept in registers
+      //      across phase 2, whose 8 x 8 accumulator tile needs them) ------------------------------
+      float2 x2[GE / 2];
 #pragma unroll
+      for (int i = 0; i < GE / 4; ++i) {
+        const float4 v = lds4g(xs + tid * XS + 4 * i);
+        x2[2 * i] = make_float2(v.x, v.y);
+        x2[2 * i + 1] = make_float2(v.z, v.w);
+      }
+#pragma unroll 1
       for (int hc = 0; hc < GH / 8; ++hc) {
         float2 pre2[8];
 #pragma unroll
@@ -283,19 +291,69 @@ __global__ void __launch_bounds__(kTile, 1) psf_gen_bwd_kernel(const GenParams p
       float* acc_m = wsc + (long long)m * kAccBlk;
       // ---- phase 2a: dW1[h][e] += sum_rows dpre[row][h] * x[row][e]  (+ db1) -----------------
       {
-        const int kg = lane & 15;                                   // row group: rows rr*16 + kg
-        const int hb = warp >> 1, eb = ((warp & 1) << 1) | (lane >> 4);
+        const int kg = lane & 7;                                    // row group: rows rr*8 + kg
+        const int t16 = (lane >> 3) | (warp << 2);                  // 16 output tiles of 8 x 8
+        const int hb = t16 >> 2, eb = t16 & 3;
         float2 v[32];  // v[i * 4 + j] = outputs (i, 2j), (i, 2j + 1) of the 8 x 8 tile
         float db[8];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) db[i] = 0.f;
-#pragma unroll 2
-        for (int rr = 0; rr < kTile / 16; ++rr) {
-          const int r = rr * 16 + kg;
+#pragma unroll 1
+        for (int rr = 0; rr < kTB / 8; ++rr) {
+          const int r = rr * 8 + kg;
           const float4 d0 = lds4g(dps + r * XS + hb * 8), d1 = lds4g(dps + r * XS + hb * 8 + 4);
           const float4 a0 = lds4g(xs + r * XS + eb * 8), a1 = lds4g(xs + r * XS + eb * 8 + 4);
+          const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+          const float2 aa[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y),
+                                make_float2(a1.z, a1.w)};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float2 di = make_float2(dd[i], dd[i]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ffma2(v[i * 4 + j], aa[j], di);
+            db[i] += dd[i];
+          }
+        }
+        rs_step2<16>(v, 4, lane & 4);
+        rs_step2<8>(v, 2, lane & 2);
+        rs_step2<4>(v, 1, lane & 1);
+        const int i = ((lane & 4) ? 4 : 0) + ((lane & 2) ? 2 : 0) + (lane & 1);   // tile row this lane ends up owning
+        float4* dst = reinterpret_cast<float4*>(acc_m + (hb * 8 + i) * GE + eb * 8);
+        float4 c0 = dst[0], c1 = dst[1];
+        c0.x += v[0].x;
+        c0.y += v[0].y;
+        c0.z += v[1].x;
+        c0.w += v[1].y;
+        c1.x += v[2].x;
+        c1.y += v[2].y;
+        c1.z += v[3].x;
+        c1.w += v[3].y;
+        dst[0] = c0;
+        dst[1] = c1;
+        // bias gradient: every lane group holds the column sums of dpre; the eb == 0 tiles write them
+        rs_step<4>(db, 4, lane & 4);
+        rs_step<2>(db, 2, lane & 2);
+        rs_step<1>(db, 1, lane & 1);
+        if (eb == 0) acc_m[GH * GE + hb * 8 + i] += db[0];
+      }
+      // ---- phase 2b: dW2[l][h] += sum_rows dout[row][l] * hid[row][h]  (+ db2) ----------------
+      {
+        const int kg = lane & 15;                                   // row group: rows rr*16 + kg
+        const int t8 = (lane >> 4) | (warp << 1);                   // 8 output tiles of 8 x 8
+        const int lb = t8 >> 2, hb = t8 & 3;
+        float2 v[32];  // v[i * 4 + j] = outputs (i, 2j), (i, 2j + 1) of the 8 x 8 tile
+        float db[8];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) db[i] = 0.f;
+#pragma unroll 1
+        for (int rr = 0; rr < kTB / 16; ++rr) {
+          const int r = rr * 16 + kg;
+          const float4 d0 = lds4g(dos + r * DS + lb * 8), d1 = lds4g(dos + r * DS + lb * 8 + 4);
+          const float4 a0 = lds4g(hs + r * XS + hb * 8), a1 = lds4g(hs + r * XS + hb * 8 + 4);
           const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
           const float2 aa[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y),
                                 make_float2(a1.z, a1.w)};
@@ -312,68 +370,19 @@ __global__ void __launch_bounds__(kTile, 1) psf_gen_bwd_kernel(const GenParams p
         rs_step2<4>(v, 2, lane & 2);
         rs_step2<2>(v, 1, lane & 1);
         const int o = ((lane & 8) ? 32 : 0) + ((lane & 4) ? 16 : 0) + ((lane & 2) ? 8 : 0) + ((lane & 1) ? 4 : 0);
-        float4* dst = reinterpret_cast<float4*>(acc_m + (hb * 8 + (o >> 3)) * GE + eb * 8 + (o & 7));
+        float4* dst = reinterpret_cast<float4*>(acc_m + GH * GE + GH + (lb * 8 + (o >> 3)) * GH + hb * 8 + (o & 7));
         float4 cur = *dst;
         cur.x += v[0].x;
         cur.y += v[0].y;
         cur.z += v[1].x;
         cur.w += v[1].y;
         *dst = cur;
-        // bias gradient: the eb == 0 half-warps hold the column sums of dpre
         rs_step<4>(db, 8, lane & 8);
         rs_step<2>(db, 4, lane & 4);
         rs_step<1>(db, 2, lane & 2);
         db[0] += __shfl_xor_sync(0xffffffffu, db[0], 1);
-        if (eb == 0 && !(lane & 1)) {
-          const int h = hb * 8 + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
-          acc_m[GH * GE + h] += db[0];
-        }
-      }
-      // ---- phase 2b: dW2[l][h] += sum_rows dout[row][l] * hid[row][h]  (+ db2) ----------------
-      {
-        const int kg = lane;                                        // row group: rows rr*32 + kg
-        const int lb = warp >> 2, hb = warp & 3;
-        float2 v[32];  // v[i * 4 + j] = outputs (i, 2j), (i, 2j + 1) of the 8 x 8 tile
-        float db[8];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) db[i] = 0.f;
-#pragma unroll 2
-        for (int rr = 0; rr < kTile / 32; ++rr) {
-          const int r = rr * 32 + kg;
-          const float4 d0 = lds4g(dos + r * DS + lb * 8), d1 = lds4g(dos + r * DS + lb * 8 + 4);
-          const float4 a0 = lds4g(hs + r * XS + hb * 8), a1 = lds4g(hs + r * XS + hb * 8 + 4);
-          const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-          const float2 aa[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y),
-                                make_float2(a1.z, a1.w)};
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float2 di = make_float2(dd[i], dd[i]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) ffma2(v[i * 4 + j], aa[j], di);
-            db[i] += dd[i];
-          }
-        }
-        rs_step2<16>(v, 16, lane & 16);
-        rs_step2<8>(v, 8, lane & 8);
-        rs_step2<4>(v, 4, lane & 4);
-        rs_step2<2>(v, 2, lane & 2);
-        rs_step2<1>(v, 1, lane & 1);
-        const int o = ((lane & 16) ? 32 : 0) + ((lane & 8) ? 16 : 0) + ((lane & 4) ? 8 : 0) + ((lane & 2) ? 4 : 0) +
-                      ((lane & 1) ? 2 : 0);
-        float2* dst = reinterpret_cast<float2*>(acc_m + GH * GE + GH + (lb * 8 + (o >> 3)) * GH + hb * 8 + (o & 7));
-        float2 cur = *dst;
-        cur.x += v[0].x;
-        cur.y += v[0].y;
-        *dst = cur;
-        rs_step<4>(db, 16, lane & 16);
-        rs_step<2>(db, 8, lane & 8);
-        rs_step<1>(db, 4, lane & 4);
-        db[0] += __shfl_xor_sync(0xffffffffu, db[0], 2);
-        db[0] += __shfl_xor_sync(0xffffffffu, db[0], 1);
-        if (hb == 0 && !(lane & 3)) {
-          const int l = lb * 8 + ((lane & 16) ? 4 : 0) + ((lane & 8) ? 2 : 0) + ((lane & 4) ? 1 : 0);
+        if (hb == 0 && !(lane & 1)) {
+          const int l = lb * 8 + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
           acc_m[GH * GE + GH + GLP * GH + l] += db[0];
         }
       }
@@ -417,7 +426,7 @@ int gen_grid(int per_sm) {
   return sms * per_sm;
 }
 
-constexpr int kSmemBwd = (3 * kTile * XS + kTile * DS + kBlkBwd) * 4;
+constexpr int kSmemBwd = (3 * kTB * XS + kTB * DS + kBlkBwd) * 4;
 
 int gen_check(int64_t rows, int n_W, int E, int H, int L) {
   if (E != GE || H != GH || L < 1 || L > GLP || n_W < 1 || rows < 1) return PSF_ERR_UNSUPPORTED;
@@ -439,7 +448,7 @@ extern "C" {
 
 size_t psf_generators_workspace_bytes(int n_W) {
   if (n_W < 1) return 0;
-  return psf_round256((size_t)gen_grid(1) * (size_t)n_W * kAccBlk * sizeof(float));
+  return psf_round256((size_t)gen_grid(3) * (size_t)n_W * kAccBlk * sizeof(float));
 }
 
 int psf_generators_fwd(const float* x, const float* W1, const float* b1, const float* W2, const float* b2, float* W_out,
@@ -481,8 +490,8 @@ int psf_generators_bwd(const float* x, const float* W1, const float* b1, const f
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(dx) & 15)) return PSF_ERR_ARG;
   if (workspace == nullptr || workspace_bytes < psf_generators_workspace_bytes(n_W)) return PSF_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
-  const long long ntiles = (rows + kTile - 1) / kTile;
-  long long grid = gen_grid(1);
+  const long long ntiles = (rows + kTB - 1) / kTB;
+  long long grid = gen_grid(3);
   if (grid > ntiles) grid = ntiles;
   if (grid < 1) grid = 1;
   PSF_CUDA_TRY(cudaMemsetAsync(workspace, 0, (size_t)grid * n_W * kAccBlk * sizeof(float), st));
@@ -501,7 +510,7 @@ int psf_generators_bwd(const float* x, const float* W1, const float* b1, const f
   p.n_W = n_W;
   p.L = L;
   if (rows > 0) {
-    psf_gen_bwd_kernel<<<(unsigned)grid, kTile, kSmemBwd, st>>>(p);
+    psf_gen_bwd_kernel<<<(unsigned)grid, kTB, kSmemBwd, st>>>(p);
     PSF_CUDA_TRY(cudaGetLastError());
   }
   psf_gen_reduce_kernel<<<(n_W * kAccBlk + 255) / 256, 256, 0, st>>>((const float*)workspace, (int)grid, n_W, L, dW1, db1,
