@@ -145,21 +145,34 @@ int psf_chain_preferred_interleave(const psf_chain_desc* d);
  * clusters), 1 (contiguous row blocks) or 0 (per-factor path). */
 int psf_chain_fused_generation(const psf_chain_desc* d);
 
-/* ---- the W generators (fs[m] = Linear(E,H) -> GELU -> Linear(H,L), psf.py:110-126, called at :175) ------
- * All n_W generators in one kernel each way, fp32 FMA.  Supported: E = H = 32, L <= 16 (else
- * PSF_ERR_UNSUPPORTED and the caller keeps its own GEMM path).
- *   x [rows,32] row-major; W1 [n_W,32,32] (out,in), b1 [n_W,32], W2 [n_W,L,32], b2 [n_W,L]  (nn.Linear layout)
- *   W_out / dW_in: element (m, l, row) at m*stride_factor + l*stride_tap + row  (the chain's tap-major layout;
- *   the row order is that of x).  Backward recomputes the hidden activations and needs
- *   psf_generators_workspace_bytes(n_W) bytes of device workspace (overwritten). */
+/* ---- the generators (fs[m] and g: Linear(E,H) -> GELU -> Linear(H,out), psf.py:110-126; called at
+ * psf.py:165 (V = g(data)) and :175 (W = fs[m](data))) -------------------------------------------------
+ * All n_W W-generators, and optionally the V generator g, in ONE kernel each way, fp32 FMA.
+ * Supported: E = H = 32, L <= 16, C <= 16 (else PSF_ERR_UNSUPPORTED and the caller keeps its own GEMM path).
+ *   x [rows,32] row-major, rows = B*n, row order given by `interleave` (1 natural; Q > 1 quad-interleaved
+ *   per sample of n rows, as in psf_chain_desc).  Parameters in nn.Linear layout: W1 [.,32,32] (out,in),
+ *   b1 [.,32], W2 [.,out,32], b2 [.,out]; `fs` tensors are stacked over the n_W generators, `g` is single.
+ *   W_out / dW_in: element (m, l, row) at m*stride_factor + l*stride_tap + row (the chain's tap-major
+ *   layout, row order = that of x).  V_out / dV_in: [rows, C] row-major in NATURAL row order (what the chain
+ *   takes as V0).  C = 0: no V generator (g pointers ignored).  The backward pass recomputes the hidden
+ *   activations and needs psf_generators_workspace_bytes(n_W) bytes of device workspace (overwritten). */
+typedef struct {
+  int64_t rows;                       /* B*n                                                   */
+  int64_t n;                          /* rows per sample (used when interleave > 1 or C > 0)   */
+  int n_W, E, H, L;
+  int64_t stride_factor, stride_tap;  /* layout of W_out / dW_in                               */
+  int interleave;                     /* row order of x and of W                               */
+  int C;                              /* outputs of the V generator g, 0 = none                */
+} psf_gen_desc;
+typedef struct { const float *W1, *b1, *W2, *b2; } psf_mlp_params;
+typedef struct { float *W1, *b1, *W2, *b2; } psf_mlp_grads;
+
 size_t psf_generators_workspace_bytes(int n_W);
-int psf_generators_fwd(const float* x, const float* W1, const float* b1, const float* W2, const float* b2,
-                       float* W_out, int64_t rows, int n_W, int E, int H, int L, int64_t stride_factor,
-                       int64_t stride_tap, psf_stream_t stream);
-int psf_generators_bwd(const float* x, const float* W1, const float* b1, const float* W2, const float* b2,
-                       const float* dW_in, float* dx, float* dW1, float* db1, float* dW2, float* db2,
-                       void* workspace, size_t workspace_bytes, int64_t rows, int n_W, int E, int H, int L,
-                       int64_t stride_factor, int64_t stride_tap, psf_stream_t stream);
+int psf_generators_fwd(const psf_gen_desc* d, const float* x, psf_mlp_params fs, psf_mlp_params g, float* W_out,
+                       float* V_out, psf_stream_t stream);
+int psf_generators_bwd(const psf_gen_desc* d, const float* x, psf_mlp_params fs, psf_mlp_params g,
+                       const float* dW_in, const float* dV_in, float* dx, psf_mlp_grads dfs, psf_mlp_grads dg,
+                       void* workspace, size_t workspace_bytes, psf_stream_t stream);
 
 /* Launch geometry the fused path would use for this problem (for benches / docs):
  * cluster size, rows per CTA, threads per CTA, dynamic SMEM bytes, resident clusters.

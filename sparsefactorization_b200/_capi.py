@@ -29,6 +29,15 @@ class ChainDesc(C.Structure):
     ]
 
 
+class GenDesc(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("n", C.c_int64), ("n_W", C.c_int), ("E", C.c_int), ("H", C.c_int), ("L", C.c_int),
+                ("stride_factor", C.c_int64), ("stride_tap", C.c_int64), ("interleave", C.c_int), ("C", C.c_int)]
+
+
+class MlpPtrs(C.Structure):       # psf_mlp_params / psf_mlp_grads (same shape)
+    _fields_ = [("W1", C.c_void_p), ("b1", C.c_void_p), ("W2", C.c_void_p), ("b2", C.c_void_p)]
+
+
 _lock = threading.Lock()
 _lib = None
 
@@ -55,10 +64,10 @@ _SIGNATURES = {
     "psf_chain_preferred_interleave": (C.c_int, [C.POINTER(ChainDesc)]),
     "psf_chain_fused_generation": (C.c_int, [C.POINTER(ChainDesc)]),
     "psf_generators_workspace_bytes": (C.c_size_t, [C.c_int]),
-    "psf_generators_fwd": (C.c_int, [C.c_void_p] * 6 + [C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
-                                                         C.c_int64, C.c_void_p]),
-    "psf_generators_bwd": (C.c_int, [C.c_void_p] * 12 + [C.c_size_t, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
-                                                          C.c_int64, C.c_int64, C.c_void_p]),
+    "psf_generators_fwd": (C.c_int, [C.POINTER(GenDesc), C.c_void_p, MlpPtrs, MlpPtrs, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]),
+    "psf_generators_bwd": (C.c_int, [C.POINTER(GenDesc), C.c_void_p, MlpPtrs, MlpPtrs, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, MlpPtrs, MlpPtrs, C.c_void_p, C.c_size_t, C.c_void_p]),
     "psf_chain_fused_plan": (C.c_int, [C.POINTER(ChainDesc), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                        C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
 }

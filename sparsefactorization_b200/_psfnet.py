@@ -169,7 +169,7 @@ def generate_factors(fs: Sequence[MLPBlock], data: torch.Tensor, interleave: int
         data = data.view(B, n // (4 * interleave), interleave, 4, E).permute(0, 2, 1, 3, 4).reshape(B, n, E)
     x_shared = data.reshape(B * n, E)
     if USE_FUSED_GENERATORS and _gen.fusable(fs, data):
-        wt = _gen.fused_generators(fs, x_shared)                   # [n_W, L, B*n], one kernel
+        wt, _ = _gen.fused_generators(fs, x_shared, n, interleave)  # [n_W, L, B*n], one kernel
         return wt.view(n_W, wt.shape[1], B, n).permute(0, 2, 3, 1)
     if not _same_structure(fs):
         # heterogeneous generators: evaluate one by one (reference order), then re-lay
@@ -206,8 +206,36 @@ def generate_factors(fs: Sequence[MLPBlock], data: torch.Tensor, interleave: int
     raise RuntimeError("generator has no Linear layer")
 
 
+def generate_all(fs: Sequence[MLPBlock], g: MLPBlock, data: torch.Tensor, interleave: int = 1):
+    """``(W, V0)``: every ``fs[m](data)`` and ``g(data)`` (psf.py:165, :175).  One fused kernel when the shapes
+    allow (W tap-major in the requested row order, V0 natural ``[B, n, C]``), else the GEMM routes."""
+    B, n, E = data.shape
+    if USE_FUSED_GENERATORS and _gen.fusable(fs, data, g):
+        xp = data
+        if interleave > 1:
+            xp = data.view(B, n // (4 * interleave), interleave, 4, E).permute(0, 2, 1, 3, 4)
+        wt, v0 = _gen.fused_generators(fs, xp.reshape(B * n, E), n, interleave, g)
+        return wt.view(len(fs), wt.shape[1], B, n).permute(0, 2, 3, 1), v0.view(B, n, -1)
+    return generate_factors(fs, data, interleave), g(data)
+
+
 class PSFChainMixin:
     """forward() tail shared by the variants: W generation + fused chain (psf.py:165-188)."""
+
+    def _chain_from_data(self, data: torch.Tensor, v_dropout=None) -> torch.Tensor:
+        """``V = g(data)`` (+ the LRA variants' dropout2), ``W_m = fs[m](data)``, then the chain."""
+        n_W, (B, n, _) = len(self.fs), data.shape
+        L = self.fs[0].network[-1].out_features
+        Cv = self.g.network[-1].out_features
+        homog = _same_structure(self.fs)
+        Q = preferred_interleave(n_W, B, n, L, Cv) if data.dtype == torch.float32 and homog else 1
+        if homog:
+            W, V = generate_all(self.fs, self.g, data, Q)
+        else:
+            W, V = generate_factors(self.fs, data, 1), self.g(data)
+        if v_dropout is not None:
+            V = v_dropout(V)
+        return chord_chain(W, V, use_residuals=self.use_residuals, interleave=Q)
 
     def _apply_chain(self, data: torch.Tensor, V: torch.Tensor) -> torch.Tensor:
         n_W, (B, n, _) = len(self.fs), data.shape

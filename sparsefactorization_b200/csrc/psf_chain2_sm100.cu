@@ -113,7 +113,6 @@ struct Geo {
   static constexpr int NQ = J / 4;  // local quads
   static constexpr int NLOC = LOGJ - 2;
   static constexpr int NREM = LOGQ;
-  static constexpr int L = 3 + NREM + NLOC;
   static constexpr int NPASS = (NT + NW - 1) / NW;
   static constexpr int NR = NREM > 0 ? NREM : 1;
   static constexpr int SKIP0 = NREM > 0 ? 0 : 1;  // local tap 0 is R(0) when there is no cluster

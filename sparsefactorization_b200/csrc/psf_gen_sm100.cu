@@ -51,12 +51,47 @@ struct GenParams {
   const float* b1;  // [n_W][32]
   const float* W2;  // [n_W][L][32]
   const float* b2;  // [n_W][L]
+  const float* gW1; // optional V generator g (psf.py:126): [32][32], [32], [C][32], [C]; generator index n_W
+  const float* gb1;
+  const float* gW2;
+  const float* gb2;
   float* Wt;        // fwd: out [n_W][L][rows];  bwd: dW (same layout, read)
+  float* V;         // fwd: V0 [rows][C] in NATURAL row order;  bwd: dV0 (read)
   float* dx;        // bwd: [rows][32]
-  float* ws;        // bwd: [grid][n_W][kAccBlk]
+  float* ws;        // bwd: [grid][n_gen][kAccBlk]
   long long rows, sWf, sWt;
   int n_W, L;
+  int n_gen;        // n_W + (g present)
+  int C;            // outputs of g
+  int n, Q;         // rows per sample and row interleave of x (to find the natural row of a V0 row)
 };
+
+// generator m's parameter tensors and output count
+__device__ __forceinline__ void gen_ptrs(const GenParams& p, int m, const float*& W1, const float*& b1, const float*& W2,
+                                         const float*& b2, int& Lm) {
+  if (m < p.n_W) {
+    W1 = p.W1 + (long long)m * GH * GE;
+    b1 = p.b1 + m * GH;
+    W2 = p.W2 + (long long)m * p.L * GH;
+    b2 = p.b2 + m * p.L;
+    Lm = p.L;
+  } else {
+    W1 = p.gW1;
+    b1 = p.gb1;
+    W2 = p.gW2;
+    b2 = p.gb2;
+    Lm = p.C;
+  }
+}
+// natural row index of row `row` of a quad-interleaved x (include/psf_b200.h)
+__device__ __forceinline__ long long natural_row(const GenParams& p, long long row) {
+  if (p.Q <= 1) return row;
+  const long long b = row / p.n;
+  const int pos = (int)(row - b * p.n);
+  const int J = p.n / p.Q;
+  const int q = pos / J, r = pos - q * J;
+  return b * p.n + 4 * ((r >> 2) * p.Q + q) + (r & 3);
+}
 
 // ---------------------------------------------------------------------------------------------
 // forward
@@ -64,20 +99,23 @@ struct GenParams {
 __global__ void __launch_bounds__(kTile, 2) psf_gen_fwd_kernel(const GenParams p) {
   extern __shared__ __align__(16) float gsm[];
   // all generators' weights -> shared memory, once per (persistent) CTA
-  for (int idx = threadIdx.x; idx < p.n_W * kBlkFwd; idx += kTile) {
+  for (int idx = threadIdx.x; idx < p.n_gen * kBlkFwd; idx += kTile) {
     const int m = idx / kBlkFwd;
     int o = idx - m * kBlkFwd;
+    const float *W1, *b1, *W2, *b2;
+    int Lm;
+    gen_ptrs(p, m, W1, b1, W2, b2, Lm);
     float v;
     if (o < GH * GE) {
-      v = p.W1[(long long)m * GH * GE + o];
+      v = W1[o];
     } else if ((o -= GH * GE) < GH) {
-      v = p.b1[m * GH + o];
+      v = b1[o];
     } else if ((o -= GH) < GH * GLP) {
       const int h = o / GLP, l = o - h * GLP;
-      v = l < p.L ? p.W2[((long long)m * p.L + l) * GH + h] : 0.f;
+      v = l < Lm ? W2[l * GH + h] : 0.f;
     } else {
       o -= GH * GLP;
-      v = o < p.L ? p.b2[m * p.L + o] : 0.f;
+      v = o < Lm ? b2[o] : 0.f;
     }
     gsm[idx] = v;
   }
@@ -98,7 +136,7 @@ __global__ void __launch_bounds__(kTile, 2) psf_gen_fwd_kernel(const GenParams p
       }
     }
 #pragma unroll 1
-    for (int m = 0; m < p.n_W; ++m) {
+    for (int m = 0; m < p.n_gen; ++m) {
       const float* w1 = gsm + m * kBlkFwd;
       const float* b1 = w1 + GH * GE;
       const float* w2t = b1 + GH;
@@ -136,10 +174,17 @@ __global__ void __launch_bounds__(kTile, 2) psf_gen_fwd_kernel(const GenParams p
           }
         }
       }
-      float* dst = p.Wt + (long long)m * p.sWf + row;
+      if (m < p.n_W) {
+        float* dst = p.Wt + (long long)m * p.sWf + row;
 #pragma unroll
-      for (int l = 0; l < GLP; ++l)
-        if (l < p.L) dst[(long long)l * p.sWt] = (l & 1) ? out2[l >> 1].y : out2[l >> 1].x;
+        for (int l = 0; l < GLP; ++l)
+          if (l < p.L) dst[(long long)l * p.sWt] = (l & 1) ? out2[l >> 1].y : out2[l >> 1].x;
+      } else {  // V0 row, natural order, row-major
+        float* dst = p.V + natural_row(p, row) * p.C;
+#pragma unroll
+        for (int c = 0; c < GLP; ++c)
+          if (c < p.C) dst[c] = (c & 1) ? out2[c >> 1].y : out2[c >> 1].x;
+      }
     }
   }
 }
@@ -181,7 +226,7 @@ __global__ void __launch_bounds__(kTB, 3) psf_gen_bwd_kernel(const GenParams p) 
   const float* w2 = b1 + GH;          // [GLP][GH], rows >= L are zero
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float* wsc = p.ws + (long long)blockIdx.x * p.n_W * kAccBlk;
+  float* wsc = p.ws + (long long)blockIdx.x * p.n_gen * kAccBlk;
   const long long ntiles = (p.rows + kTB - 1) / kTB;
 
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -199,26 +244,38 @@ __global__ void __launch_bounds__(kTB, 3) psf_gen_bwd_kernel(const GenParams p) 
 #pragma unroll
     for (int i = 0; i < GE / 4; ++i) *reinterpret_cast<float4*>(xs + tid * XS + 4 * i) = xin[i];
 
+    const long long nat = (live && p.n_gen > p.n_W) ? natural_row(p, row) : 0;
 #pragma unroll 1
-    for (int m = 0; m < p.n_W; ++m) {
+    for (int m = 0; m < p.n_gen; ++m) {
       __syncthreads();  // phase 2 of the previous generator is done with dps / hs / dos and the weights
-      for (int o = tid; o < kBlkBwd; o += kTB) {
-        float v;
-        if (o < GH * GE) {
-          v = p.W1[(long long)m * GH * GE + o];
-        } else if (o < GH * GE + GH) {
-          v = p.b1[m * GH + (o - GH * GE)];
-        } else {
-          const int q = o - GH * GE - GH, l = q / GH;
-          v = l < p.L ? p.W2[(long long)m * p.L * GH + q] : 0.f;
+      {
+        const float *W1, *b1g, *W2, *b2g;
+        int Lm;
+        gen_ptrs(p, m, W1, b1g, W2, b2g, Lm);
+        for (int o = tid; o < kBlkBwd; o += kTB) {
+          float v;
+          if (o < GH * GE) {
+            v = W1[o];
+          } else if (o < GH * GE + GH) {
+            v = b1g[o - GH * GE];
+          } else {
+            const int q = o - GH * GE - GH, l = q / GH;
+            v = l < Lm ? W2[q] : 0.f;
+          }
+          wb[o] = v;
         }
-        wb[o] = v;
       }
       float dout[GLP];
       {
-        const float* src = p.Wt + (long long)m * p.sWf + row;
+        if (m < p.n_W) {
+          const float* src = p.Wt + (long long)m * p.sWf + row;
 #pragma unroll
-        for (int l = 0; l < GLP; ++l) dout[l] = (live && l < p.L) ? __ldcs(src + (long long)l * p.sWt) : 0.f;
+          for (int l = 0; l < GLP; ++l) dout[l] = (live && l < p.L) ? __ldcs(src + (long long)l * p.sWt) : 0.f;
+        } else {
+          const float* src = p.V + nat * p.C;
+#pragma unroll
+          for (int c = 0; c < GLP; ++c) dout[c] = (live && c < p.C) ? __ldcs(src + c) : 0.f;
+        }
 #pragma unroll
         for (int i = 0; i < GLP / 4; ++i)
           *reinterpret_cast<float4*>(dos + tid * DS + 4 * i) = make_float4(dout[4 * i], dout[4 * i + 1], dout[4 * i + 2], dout[4 * i + 3]);
@@ -396,24 +453,33 @@ __global__ void __launch_bounds__(kTB, 3) psf_gen_bwd_kernel(const GenParams p) 
 }
 
 // sum the per-CTA slices in a fixed order and scatter into the parameter-gradient tensors
-__global__ void psf_gen_reduce_kernel(const float* __restrict__ ws, int nslices, int n_W, int L, float* __restrict__ dW1,
-                                      float* __restrict__ db1, float* __restrict__ dW2, float* __restrict__ db2) {
-  const int total = n_W * kAccBlk;
+struct GenGrads {
+  float *W1, *b1, *W2, *b2;     // stacked [n_W, ...]
+  float *gW1, *gb1, *gW2, *gb2; // the V generator (generator index n_W), may be null
+};
+__global__ void psf_gen_reduce_kernel(const float* __restrict__ ws, int nslices, int n_W, int n_gen, int L, int C,
+                                      GenGrads g) {
+  const int total = n_gen * kAccBlk;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     float s = 0.f;
     for (int c = 0; c < nslices; ++c) s += ws[(long long)c * total + idx];
     const int m = idx / kAccBlk;
     int o = idx - m * kAccBlk;
+    const bool isg = m >= n_W;
+    float* dW1 = isg ? g.gW1 : g.W1 + (long long)m * GH * GE;
+    float* db1 = isg ? g.gb1 : g.b1 + m * GH;
+    float* dW2 = isg ? g.gW2 : g.W2 + (long long)m * L * GH;
+    float* db2 = isg ? g.gb2 : g.b2 + m * L;
+    const int Lm = isg ? C : L;
     if (o < GH * GE) {
-      dW1[(long long)m * GH * GE + o] = s;
+      dW1[o] = s;
     } else if ((o -= GH * GE) < GH) {
-      db1[m * GH + o] = s;
+      db1[o] = s;
     } else if ((o -= GH) < GLP * GH) {
-      const int l = o / GH;
-      if (l < L) dW2[((long long)m * L + l) * GH + (o - l * GH)] = s;
+      if (o / GH < Lm) dW2[o] = s;
     } else {
       o -= GLP * GH;
-      if (o < L) db2[m * L + o] = s;
+      if (o < Lm) db2[o] = s;
     }
   }
 }
@@ -448,73 +514,86 @@ extern "C" {
 
 size_t psf_generators_workspace_bytes(int n_W) {
   if (n_W < 1) return 0;
-  return psf_round256((size_t)gen_grid(3) * (size_t)n_W * kAccBlk * sizeof(float));
+  return psf_round256((size_t)gen_grid(3) * (size_t)(n_W + 1) * kAccBlk * sizeof(float));
 }
 
-int psf_generators_fwd(const float* x, const float* W1, const float* b1, const float* W2, const float* b2, float* W_out,
-                       int64_t rows, int n_W, int E, int H, int L, int64_t stride_factor, int64_t stride_tap,
-                       psf_stream_t stream) {
-  if (x == nullptr || W1 == nullptr || b1 == nullptr || W2 == nullptr || b2 == nullptr || W_out == nullptr) return PSF_ERR_ARG;
-  if (rows == 0) return PSF_OK;
-  int rc = gen_check(rows, n_W, E, H, L);
+static int gen_fill(GenParams& p, const psf_gen_desc* d, const float* x, const psf_mlp_params& fs, const psf_mlp_params& g) {
+  if (d == nullptr || x == nullptr || fs.W1 == nullptr || fs.b1 == nullptr || fs.W2 == nullptr || fs.b2 == nullptr)
+    return PSF_ERR_ARG;
+  const bool has_g = d->C > 0;
+  if (has_g && (g.W1 == nullptr || g.b1 == nullptr || g.W2 == nullptr || g.b2 == nullptr)) return PSF_ERR_ARG;
+  if (d->C < 0 || d->C > GLP) return PSF_ERR_UNSUPPORTED;
+  const int Q = d->interleave < 1 ? 1 : d->interleave;
+  if ((has_g || Q > 1) && (d->n < 1 || d->rows % d->n != 0 || (Q > 1 && d->n % (4 * (int64_t)Q) != 0))) return PSF_ERR_ARG;
+  int rc = gen_check(d->rows < 1 ? 1 : d->rows, d->n_W + (has_g ? 1 : 0), d->E, d->H, d->L);
   if (rc) return rc;
   if (reinterpret_cast<uintptr_t>(x) & 15) return PSF_ERR_ARG;
-  GenParams p = {};
   p.x = x;
-  p.W1 = W1;
-  p.b1 = b1;
-  p.W2 = W2;
-  p.b2 = b2;
+  p.W1 = fs.W1;
+  p.b1 = fs.b1;
+  p.W2 = fs.W2;
+  p.b2 = fs.b2;
+  p.gW1 = g.W1;
+  p.gb1 = g.b1;
+  p.gW2 = g.W2;
+  p.gb2 = g.b2;
+  p.rows = d->rows;
+  p.sWf = d->stride_factor;
+  p.sWt = d->stride_tap;
+  p.n_W = d->n_W;
+  p.L = d->L;
+  p.n_gen = d->n_W + (has_g ? 1 : 0);
+  p.C = d->C;
+  p.n = (int)(d->n < 1 ? 1 : d->n);
+  p.Q = Q;
+  return PSF_OK;
+}
+
+int psf_generators_fwd(const psf_gen_desc* d, const float* x, psf_mlp_params fs, psf_mlp_params g, float* W_out,
+                       float* V_out, psf_stream_t stream) {
+  GenParams p = {};
+  int rc = gen_fill(p, d, x, fs, g);
+  if (rc) return rc;
+  if (W_out == nullptr || (d->C > 0 && V_out == nullptr)) return PSF_ERR_ARG;
+  if (d->rows == 0) return PSF_OK;
   p.Wt = W_out;
-  p.rows = rows;
-  p.sWf = stride_factor;
-  p.sWt = stride_tap;
-  p.n_W = n_W;
-  p.L = L;
-  const long long ntiles = (rows + kTile - 1) / kTile;
+  p.V = V_out;
+  const long long ntiles = (d->rows + kTile - 1) / kTile;
   long long grid = gen_grid(2);
   if (grid > ntiles) grid = ntiles;
-  psf_gen_fwd_kernel<<<(unsigned)grid, kTile, (size_t)n_W * kBlkFwd * 4, (cudaStream_t)stream>>>(p);
+  psf_gen_fwd_kernel<<<(unsigned)grid, kTile, (size_t)p.n_gen * kBlkFwd * 4, (cudaStream_t)stream>>>(p);
   return (int)cudaGetLastError();
 }
 
-int psf_generators_bwd(const float* x, const float* W1, const float* b1, const float* W2, const float* b2,
-                       const float* dW_in, float* dx, float* dW1, float* db1, float* dW2, float* db2, void* workspace,
-                       size_t workspace_bytes, int64_t rows, int n_W, int E, int H, int L, int64_t stride_factor,
-                       int64_t stride_tap, psf_stream_t stream) {
-  if (x == nullptr || W1 == nullptr || b1 == nullptr || W2 == nullptr || b2 == nullptr || dW_in == nullptr ||
-      dx == nullptr || dW1 == nullptr || db1 == nullptr || dW2 == nullptr || db2 == nullptr)
-    return PSF_ERR_ARG;
-  int rc = gen_check(rows < 1 ? 1 : rows, n_W, E, H, L);
+int psf_generators_bwd(const psf_gen_desc* d, const float* x, psf_mlp_params fs, psf_mlp_params g, const float* dW_in,
+                       const float* dV_in, float* dx, psf_mlp_grads dfs, psf_mlp_grads dg, void* workspace,
+                       size_t workspace_bytes, psf_stream_t stream) {
+  GenParams p = {};
+  int rc = gen_fill(p, d, x, fs, g);
   if (rc) return rc;
-  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(dx) & 15)) return PSF_ERR_ARG;
-  if (workspace == nullptr || workspace_bytes < psf_generators_workspace_bytes(n_W)) return PSF_ERR_WORKSPACE;
+  if (dW_in == nullptr || dx == nullptr || dfs.W1 == nullptr || dfs.b1 == nullptr || dfs.W2 == nullptr || dfs.b2 == nullptr)
+    return PSF_ERR_ARG;
+  if (d->C > 0 && (dV_in == nullptr || dg.W1 == nullptr || dg.b1 == nullptr || dg.W2 == nullptr || dg.b2 == nullptr))
+    return PSF_ERR_ARG;
+  if (reinterpret_cast<uintptr_t>(dx) & 15) return PSF_ERR_ARG;
+  if (workspace == nullptr || workspace_bytes < psf_generators_workspace_bytes(d->n_W)) return PSF_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
-  const long long ntiles = (rows + kTB - 1) / kTB;
+  const long long ntiles = (d->rows + kTB - 1) / kTB;
   long long grid = gen_grid(3);
   if (grid > ntiles) grid = ntiles;
   if (grid < 1) grid = 1;
-  PSF_CUDA_TRY(cudaMemsetAsync(workspace, 0, (size_t)grid * n_W * kAccBlk * sizeof(float), st));
-  GenParams p = {};
-  p.x = x;
-  p.W1 = W1;
-  p.b1 = b1;
-  p.W2 = W2;
-  p.b2 = b2;
+  PSF_CUDA_TRY(cudaMemsetAsync(workspace, 0, (size_t)grid * p.n_gen * kAccBlk * sizeof(float), st));
   p.Wt = const_cast<float*>(dW_in);
+  p.V = const_cast<float*>(dV_in);
   p.dx = dx;
   p.ws = (float*)workspace;
-  p.rows = rows;
-  p.sWf = stride_factor;
-  p.sWt = stride_tap;
-  p.n_W = n_W;
-  p.L = L;
-  if (rows > 0) {
+  if (d->rows > 0) {
     psf_gen_bwd_kernel<<<(unsigned)grid, kTB, kSmemBwd, st>>>(p);
     PSF_CUDA_TRY(cudaGetLastError());
   }
-  psf_gen_reduce_kernel<<<(n_W * kAccBlk + 255) / 256, 256, 0, st>>>((const float*)workspace, (int)grid, n_W, L, dW1, db1,
-                                                                    dW2, db2);
+  GenGrads gg = {dfs.W1, dfs.b1, dfs.W2, dfs.b2, dg.W1, dg.b1, dg.W2, dg.b2};
+  psf_gen_reduce_kernel<<<(p.n_gen * kAccBlk + 255) / 256, 256, 0, st>>>((const float*)workspace, (int)grid, p.n_W, p.n_gen,
+                                                                         p.L, p.C, gg);
   return (int)cudaGetLastError();
 }
 

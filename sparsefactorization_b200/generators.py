@@ -1,22 +1,23 @@
-"""All W generators of a PSFNet in one fused CUDA kernel each way.
+"""All generators of a PSFNet in one fused CUDA kernel each way.
 
-Replaces the per-factor ``fs[m](data)`` calls of the reference (SyntheticExperiments/psf.py:110-126, :175):
-``Linear(E,H) -> GELU -> Linear(H,L)`` for every m, writing W directly in the chain's streaming
-(tap-major) layout.  fp32 FMA arithmetic (no TF32); the backward pass recomputes the hidden activations.
-Shapes the kernel does not cover (E or H != 32, L > 16, other layer stacks) stay on the batched-GEMM path
-of ``_psfnet.generate_factors``.  CUDA only.
+Replaces the per-factor ``fs[m](data)`` calls and ``g(data)`` of the reference
+(SyntheticExperiments/psf.py:110-126, :165, :175): ``Linear(E,H) -> GELU -> Linear(H,out)`` for every
+W generator and for the V generator, writing W directly in the chain's streaming (tap-major) layout and
+V0 in its natural ``[B, n, C]`` layout.  fp32 FMA arithmetic (no TF32); the backward pass recomputes the
+hidden activations.  Shapes the kernel does not cover (E or H != 32, more than 16 outputs, other layer
+stacks) stay on the batched-GEMM path of ``_psfnet.generate_factors``.  CUDA only.
 """
 from __future__ import annotations
 
 import ctypes as C
-from typing import Sequence
+from typing import Optional, Sequence
 
 import torch
 from torch import nn
 
 from . import _capi
 
-E_FUSED, H_FUSED, L_MAX = 32, 32, 16
+E_FUSED, H_FUSED, OUT_MAX = 32, 32, 16
 
 
 class _Stats:
@@ -27,75 +28,96 @@ class _Stats:
 stats = _Stats()
 
 
-def fusable(fs: Sequence[nn.Module], data: torch.Tensor) -> bool:
-    """True when every generator is Linear(32,32) -> exact GELU -> Linear(32, L <= 16) on fp32 CUDA data."""
+def _mlp_ok(f: nn.Module) -> Optional[int]:
+    """out width if ``f.network`` is Linear(32,32) -> exact GELU -> Linear(32, out <= 16) in fp32, else None."""
+    net = getattr(f, "network", None)
+    if net is None or len(net) != 3:
+        return None
+    a, act, b = net
+    if not (isinstance(a, nn.Linear) and isinstance(act, nn.GELU) and isinstance(b, nn.Linear)):
+        return None
+    if getattr(act, "approximate", "none") != "none" or a.bias is None or b.bias is None:
+        return None
+    if (a.in_features, a.out_features, b.in_features) != (E_FUSED, H_FUSED, H_FUSED) or b.out_features > OUT_MAX:
+        return None
+    if a.weight.dtype != torch.float32 or not a.weight.is_cuda:
+        return None
+    return b.out_features
+
+
+def fusable(fs: Sequence[nn.Module], data: torch.Tensor, g: Optional[nn.Module] = None) -> bool:
+    """True when every generator (and ``g`` if given) has the fused kernel's shape, on fp32 CUDA data."""
     if not (data.is_cuda and data.dtype == torch.float32 and data.shape[-1] == E_FUSED and len(fs) >= 1):
         return False
-    L = None
-    for f in fs:
-        net = getattr(f, "network", None)
-        if net is None or len(net) != 3:
-            return False
-        a, act, b = net
-        if not (isinstance(a, nn.Linear) and isinstance(act, nn.GELU) and isinstance(b, nn.Linear)):
-            return False
-        if getattr(act, "approximate", "none") != "none" or a.bias is None or b.bias is None:
-            return False
-        if (a.in_features, a.out_features, b.in_features) != (E_FUSED, H_FUSED, H_FUSED) or b.out_features > L_MAX:
-            return False
-        if L is not None and b.out_features != L:
-            return False
-        L = b.out_features
-        if a.weight.dtype != torch.float32:
-            return False
-    return True
+    outs = {_mlp_ok(f) for f in fs}
+    if len(outs) != 1 or None in outs:
+        return False
+    return g is None or _mlp_ok(g) is not None
+
+
+def _ptrs(ts):
+    return _capi.MlpPtrs(*[t.data_ptr() if t is not None else None for t in ts])
 
 
 class _FusedGenerators(torch.autograd.Function):
-    """x [rows,32], w1 [n_W,32,32], b1 [n_W,32], w2 [n_W,L,32], b2 [n_W,L]  ->  W [n_W, L, rows]."""
+    """x [rows,32]; fs params stacked (w1 [n_W,32,32], b1 [n_W,32], w2 [n_W,L,32], b2 [n_W,L]); optional g params
+    ->  W [n_W, L, rows] (row order of x) and V0 [rows, C] (natural row order; empty without g)."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2):
+    def forward(ctx, x, n, interleave, w1, b1, w2, b2, gw1, gb1, gw2, gb2):
         lib = _capi.load()
         x, w1, b1, w2, b2 = (t.contiguous() for t in (x, w1, b1, w2, b2))
+        has_g = gw1 is not None
+        gs = tuple(t.contiguous() for t in (gw1, gb1, gw2, gb2)) if has_g else (None,) * 4
         rows = x.shape[0]
         n_W, L = w2.shape[0], w2.shape[1]
+        Cg = gs[2].shape[0] if has_g else 0
+        d = _capi.GenDesc(rows, n, n_W, E_FUSED, H_FUSED, L, L * rows, rows, int(interleave), Cg)
         out = torch.empty(n_W, L, rows, dtype=torch.float32, device=x.device)
+        v0 = torch.empty(rows, Cg, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
-            rc = lib.psf_generators_fwd(x.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
-                                        out.data_ptr(), rows, n_W, E_FUSED, H_FUSED, L, L * rows, rows,
-                                        torch.cuda.current_stream().cuda_stream)
+            rc = lib.psf_generators_fwd(C.byref(d), x.data_ptr(), _ptrs((w1, b1, w2, b2)), _ptrs(gs), out.data_ptr(),
+                                        v0.data_ptr() if has_g else None, torch.cuda.current_stream().cuda_stream)
         _capi.check(rc, "psf_generators_fwd")
         stats.launches += 1
-        ctx.save_for_backward(x, w1, b1, w2, b2)
-        return out
+        ctx.save_for_backward(x, w1, b1, w2, b2, *(gs if has_g else ()))
+        ctx.desc = d
+        ctx.has_g = has_g
+        return out, v0
 
     @staticmethod
     @torch.autograd.function.once_differentiable
-    def backward(ctx, dout):
+    def backward(ctx, dout, dv0):
         lib = _capi.load()
-        x, w1, b1, w2, b2 = ctx.saved_tensors
+        saved = ctx.saved_tensors
+        x, w1, b1, w2, b2 = saved[:5]
+        gs = saved[5:] if ctx.has_g else (None,) * 4
         dout = dout.contiguous()
-        rows = x.shape[0]
-        n_W, L = w2.shape[0], w2.shape[1]
+        dv0 = dv0.contiguous() if ctx.has_g else None
         dx = torch.empty_like(x)
-        dw1, db1, dw2, db2 = (torch.empty_like(t) for t in (w1, b1, w2, b2))
+        dfs = tuple(torch.empty_like(t) for t in (w1, b1, w2, b2))
+        dgs = tuple(torch.empty_like(t) for t in gs) if ctx.has_g else (None,) * 4
+        d = ctx.desc
         with torch.cuda.device(x.device):
-            nbytes = int(lib.psf_generators_workspace_bytes(n_W))
+            nbytes = int(lib.psf_generators_workspace_bytes(d.n_W))
             ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=x.device)
-            rc = lib.psf_generators_bwd(x.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
-                                        dout.data_ptr(), dx.data_ptr(), dw1.data_ptr(), db1.data_ptr(), dw2.data_ptr(),
-                                        db2.data_ptr(), ws.data_ptr(), ws.numel(), rows, n_W, E_FUSED, H_FUSED, L,
-                                        L * rows, rows, torch.cuda.current_stream().cuda_stream)
+            rc = lib.psf_generators_bwd(C.byref(d), x.data_ptr(), _ptrs((w1, b1, w2, b2)), _ptrs(gs), dout.data_ptr(),
+                                        dv0.data_ptr() if ctx.has_g else None, dx.data_ptr(), _ptrs(dfs), _ptrs(dgs),
+                                        ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
         _capi.check(rc, "psf_generators_bwd")
         stats.launches += 2
-        return dx, dw1, db1, dw2, db2
+        return (dx, None, None, *dfs, *dgs)
 
 
-def fused_generators(fs: Sequence[nn.Module], x2d: torch.Tensor) -> torch.Tensor:
-    """``W[m, l, row] = fs[m](x2d)[row, l]`` for every generator; x2d ``[rows, 32]``; result ``[n_W, L, rows]``."""
+def fused_generators(fs: Sequence[nn.Module], x2d: torch.Tensor, n: int, interleave: int = 1,
+                     g: Optional[nn.Module] = None):
+    """``W[m, l, row] = fs[m](x2d)[row, l]`` for every generator (x2d ``[rows, 32]``, result ``[n_W, L, rows]``) and,
+    with ``g``, ``V0 = g(x2d)`` as ``[rows, C]`` in natural row order (x2d rows are quad-interleaved per sample of
+    ``n`` rows when ``interleave > 1``)."""
     w1 = torch.stack([f.network[0].weight for f in fs], 0)
     b1 = torch.stack([f.network[0].bias for f in fs], 0)
     w2 = torch.stack([f.network[2].weight for f in fs], 0)
     b2 = torch.stack([f.network[2].bias for f in fs], 0)
-    return _FusedGenerators.apply(x2d, w1, b1, w2, b2)
+    gp = (g.network[0].weight, g.network[0].bias, g.network[2].weight, g.network[2].bias) if g is not None else (None,) * 4
+    W, V0 = _FusedGenerators.apply(x2d, n, interleave, w1, b1, w2, b2, *gp)
+    return W, (V0 if g is not None else None)

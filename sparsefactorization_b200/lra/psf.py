@@ -99,9 +99,7 @@ class PSFNet(PSFChainMixin, nn.Module):
             positions = torch.arange(0, self.n_vec, device=data.device).expand(data.size(0), self.n_vec)
             data = data + self.pos_embedding(positions)
         data = self.dropout1(data)
-        V = self.g(data)
-        V = self.dropout2(V)
-        V = self._apply_chain(data, V)
+        V = self._chain_from_data(data, self.dropout2)   # V = dropout2(g(data)), then the factor chain
         V = self.dropout3(V)
         if self.pooling_type == 'CLS':
             V = V[:, 0, :]

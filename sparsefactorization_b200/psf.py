@@ -69,6 +69,5 @@ class PSFNet(PSFChainMixin, nn.Module):
         if self.use_pos_embedding:
             positions = torch.arange(0, self.n_vec, device=data.device).expand(data.size(0), self.n_vec)
             data = data + self.pos_embedding(positions)
-        V = self.g(data)
-        V = self._apply_chain(data, V)          # all n_W factors (+ residual V_0 after each)
+        V = self._chain_from_data(data)         # V = g(data), all n_W factors (+ residual V_0 after each)
         return self.final(V.reshape(V.size(0), -1))

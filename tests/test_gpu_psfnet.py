@@ -178,3 +178,46 @@ def test_fused_generators_full_size_equal_gemm_route():
     torch.testing.assert_close(res[True][1], res[False][1], rtol=1e-4, atol=1e-7)
     for a, b in zip(res[True][2], res[False][2]):
         torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5 * float(b.abs().max()))
+
+
+@pytest.mark.parametrize("B,n,n_W,L,C,Q", [(2, 256, 3, 9, 8, 1), (2, 256, 4, 9, 8, 4), (1, 1024, 2, 11, 16, 8),
+                                           (3, 128, 2, 8, 3, 2)])
+def test_fused_generators_with_v_generator(B, n, n_W, L, C, Q):
+    """generate_all: every fs[m](data) and g(data) from one kernel; W comes out in the requested (quad-interleaved)
+    row order, V0 in natural order; all gradients against the per-module fp64 evaluation."""
+    from sparsefactorization_b200 import chain, generators
+    from sparsefactorization_b200._psfnet import MLPBlock, generate_all
+    torch.manual_seed(B * n + L + Q)
+    fs = torch.nn.ModuleList([MLPBlock([32, "GELU"], 32, L) for _ in range(n_W)]).cuda()
+    g = MLPBlock([32, "GELU"], 32, C).cuda()
+    data = torch.randn(B, n, 32, device="cuda", requires_grad=True)
+    gW = torch.randn(n_W, B, n, L, device="cuda") / n       # gradient w.r.t. W in NATURAL row order
+    gV = torch.randn(B, n, C, device="cuda") / n
+    perm = chain.row_permutation(n, Q, "cuda")
+    assert generators.fusable(fs, data, g)
+    before = generators.stats.launches
+    W, V0 = generate_all(fs, g, data, Q)
+    assert generators.stats.launches == before + 1
+    assert W.shape == (n_W, B, n, L) and W.stride(2) == 1 and V0.shape == (B, n, C)
+    (W * gW[:, :, perm, :]).sum().add((V0 * gV).sum()).backward()
+
+    mods64 = torch.nn.ModuleList([MLPBlock([32, "GELU"], 32, L) for _ in range(n_W)] + [MLPBlock([32, "GELU"], 32, C)])
+    mods64 = mods64.cuda().double()
+    sd = {f"{i}.{k}": v.double() for i, f in enumerate(list(fs) + [g]) for k, v in f.state_dict().items()}
+    mods64.load_state_dict(sd)
+    d64 = data.detach().double().requires_grad_(True)
+    W64 = torch.stack([f(d64) for f in mods64[:n_W]], 0)
+    V64 = mods64[n_W](d64)
+    ((W64 * gW.double()).sum() + (V64 * gV.double()).sum()).backward()
+
+    torch.testing.assert_close(W.detach(), W64[:, :, perm, :].float(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(V0.detach(), V64.float(), rtol=1e-5, atol=1e-6)
+
+    def close(a, b, what):
+        scale = float(b.abs().max())
+        torch.testing.assert_close(a.double(), b, rtol=1e-4, atol=2e-6 * scale + 1e-9, msg=lambda m: f"{what}: {m}")
+
+    close(data.grad, d64.grad, "d data")
+    for (name, p32), p64 in zip(list(fs.named_parameters()) + [("g." + k, v) for k, v in g.named_parameters()],
+                                mods64.parameters()):
+        close(p32.grad, p64.grad, name)
