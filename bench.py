@@ -11,8 +11,10 @@ fused Adam step.  One JSON line is printed by rank 0:
 
   value      whole-job seq/s with the batch resident in HBM (CUDA events, max over ranks)
   e2e        same step fed from pinned HOST buffers: H2D of X, Y and D2H of the loss inside the timed region
-  roofline   the dominant kernel (psf_chain_bwd_kernel): algorithmic bytes / measured launch time vs
-             the measured HBM copy peak (MEASURED_PEAKS.json); `chain` holds fwd, bwd and fwd+bwd figures
+  roofline   the dominant kernel of the chord-chain path BASELINE.json's metric names (psf_chain2_bwd_kernel):
+             algorithmic bytes / measured launch time vs the measured HBM copy peak (MEASURED_PEAKS.json);
+             `chain` holds fwd, bwd and fwd+bwd figures
+  generators the fused W/V generator kernels (FP32-FMA bound; they are the larger share of the step)
   cpu_baseline  the CPU oracle (oracle/, torch on the host cores) on a bounded sample of the same workload
   clocks     SM clock / throttle reasons sampled during the timed region (NVML)
 
@@ -165,7 +167,7 @@ class ClockSampler(threading.Thread):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from sparsefactorization_b200 import chain, data, dp as dpmod
+    from sparsefactorization_b200 import chain, data, dp as dpmod, generators
     from sparsefactorization_b200.psf import PSFNet
     from sparsefactorization_b200.psf_utils import seed_everything
 
@@ -220,10 +222,15 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     chain.stats.reset(timing=True)
+    generators.stats.reset(timing=True)
     total_ms = timed(lambda: step(X, Y), args.steps)
-    launches = chain.stats.launches
+    launches = chain.stats.launches + generators.stats.launches     # kernels of libpsf_b200.so in the timed region
     t_fwd, t_bwd = chain.stats.mean_ms("fwd"), chain.stats.mean_ms("bwd")
+    g_fwd, g_bwd = generators.stats.mean_ms("fwd"), generators.stats.mean_ms("bwd")
     chain.stats.reset(timing=False)
+    generators.stats.reset(timing=False)
+    plan_gen = chain.fused_generation(N_W, B, N_VEC, N_W + 1, C_V,
+                                      interleave=chain.preferred_interleave(N_W, B, N_VEC, N_W + 1, C_V))
     clocks = sampler.stop()
 
     # end to end: host buffers in, loss out, every step
@@ -247,12 +254,12 @@ def run_ours(args):
     traffic = None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "r01_chain_traffic.json")))
-        if prof.get("batch") == B:
+        if prof.get("batch") == B and prof.get("generation") == plan_gen:
             traffic = prof.get("bwd_dram_bytes_per_launch")
     except Exception:
         pass
     roofline = {
-        "kernel": "psf_chain_bwd_kernel", "bound": "hbm", "achieved": round(gbs(bb, t_bwd), 1), "peak": peak,
+        "kernel": "psf_chain2_bwd_kernel" if plan_gen == 2 else "psf_chain_bwd_kernel", "bound": "hbm", "achieved": round(gbs(bb, t_bwd), 1), "peak": peak,
         "unit": "GB/s", "frac": round(gbs(bb, t_bwd) / peak, 4), "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": B * bb, "launch_ms": round(t_bwd, 4),
         "chain": {"fwd_ms": round(t_fwd, 4), "bwd_ms": round(t_bwd, 4), "fwd_GBps": round(gbs(fb, t_fwd), 1),
@@ -260,6 +267,14 @@ def run_ours(args):
                   "fwd_bwd_frac": round(gbs(fb + bb, t_fwd + t_bwd) / peak, 4),
                   "share_of_step": round((t_fwd + t_bwd) * args.steps / total_ms, 4)},
     }
+    # the W/V generators (15 small MLPs per row) are FP32-FMA work, not HBM work: reported next to the chain
+    gen_flop = 2.0 * B * N_VEC * (N_W * (EMB * 32 + 32 * (N_W + 1)) + EMB * 32 + 32 * C_V)        # forward
+    gen_flop_bwd = 2.0 * gen_flop + 2.0 * B * N_VEC * (N_W + 1) * EMB * 32                         # + recompute
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+    gen_stats = {"kernels": "psf_gen_fwd_kernel / psf_gen_bwd_kernel", "bound": "fp32 fma (no tensor cores: fp32 parity)",
+                 "fwd_ms": round(g_fwd, 4), "bwd_ms": round(g_bwd, 4),
+                 "fwd_TFLOPs": round(gen_flop / g_fwd / 1e9, 2), "bwd_TFLOPs": round(gen_flop_bwd / g_bwd / 1e9, 2),
+                 "fp32_peak_TFLOPs": round(fp32_peak, 1), "share_of_step": round((g_fwd + g_bwd) * args.steps / total_ms, 4)}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         val, ms, threads = cpu_oracle_seqs_per_sec(args.ref_batch, 2, 1)
@@ -274,12 +289,13 @@ def run_ours(args):
                                "backward + Adam (BASELINE configs[1])",
                    "n": N_VEC, "n_W": N_W, "links": N_W + 1, "channels": C_V, "embedding": EMB,
                    "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                   "optimizer_in_step": True,
+                   "optimizer_in_step": True, "chain_kernel_generation": plan_gen,
                    "l2": "inputs larger than L2: the W stream alone is 13.8 MB/sequence x batch >> 126 MB"},
         "e2e": {"value": round(B * world * args.steps / e2e_ms * 1e3, 2), "unit": UNIT,
                 "h2d_bytes_per_step": int(Xh.numel() * 4 + Yh.numel() * 4) * world, "d2h_bytes_per_step": 4 * world},
         "gpu_launches": launches,
         "roofline": roofline,
+        "generators": gen_stats,
         "cpu_baseline": cpu,
         "clocks": clocks,
     }

@@ -29,7 +29,6 @@ constexpr int GLP = 16;   // taps padded
 constexpr int kBlkFwd = GH * GE + GH + GH * GLP + GLP;  // w1[h][e], b1[h], w2t[h][l], b2[l]  = 1584 floats
 constexpr int kBlkBwd = GH * GE + GH + GLP * GH;        // w1[h][e], b1[h], w2[l][h]          = 1568 floats
 constexpr int kAccBlk = GH * GE + GH + GLP * GH + GLP;  // dW1, db1, dW2 (l-major, padded), db2 = 1584 floats
-constexpr int kTile = 256;                               // forward: rows per tile == threads per CTA
 constexpr int kTB = 128;                                 // backward: rows per tile == threads per CTA (3 CTAs per SM)
 constexpr int XS = GE + 4;                               // padded row stride of the staged tiles (bank-conflict free)
 constexpr int DS = GLP + 4;
@@ -44,6 +43,31 @@ __device__ __forceinline__ float4 lds4g(const float* p) { return *reinterpret_ca
 
 // exact GELU as ATen evaluates it in fp32: x * 0.5 * (1 + erf(x / sqrt 2))
 __device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f)); }
+
+// Backward-only evaluation of Phi(x) and phi(x) (the standard normal cdf / pdf) for gelu(x) = x Phi(x) and
+// gelu'(x) = Phi(x) + x phi(x): erf by Abramowitz-Stegun 7.1.26 shares its exp(-x^2/2) with phi; absolute error
+// 3e-7 in fp32, which only reaches gradients (the forward kernel uses erff).  ~16 instructions instead of ~44.
+__device__ __forceinline__ void normal_cdf_pdf_fast(float x, float& cdf, float& pdf) {
+  const float e = __expf(-0.5f * x * x);
+  const float t = __fdividef(1.f, fmaf(0.23164189f, fabsf(x), 1.f));  // 0.3275911 / sqrt 2
+  float q = fmaf(1.061405429f, t, -1.453152027f);
+  q = fmaf(q, t, 1.421413741f);
+  q = fmaf(q, t, -0.284496736f);
+  q = fmaf(q, t, 0.254829592f);
+  const float half_erf = fmaf(-0.5f * q * t, e, 0.5f);  // 0.5 erf(|x| / sqrt 2)
+  cdf = 0.5f + copysignf(half_erf, x);
+  pdf = 0.39894228040143267794f * e;
+}
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
 struct GenParams {
   const float* x;
@@ -94,12 +118,16 @@ __device__ __forceinline__ long long natural_row(const GenParams& p, long long r
 }
 
 // ---------------------------------------------------------------------------------------------
-// forward
+// forward: thread = TWO rows (rows r and r + kFT of a 2*kFT-row tile), so that every broadcast weight quad
+// read from shared memory feeds 8 FMAs instead of 4 - with one row per thread the kernel sat at 90 % of the
+// shared-memory pipe (a broadcast LDS.128 costs two wavefronts).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTile, 2) psf_gen_fwd_kernel(const GenParams p) {
+constexpr int kFT = 192;  // threads per CTA; 2 CTAs per SM at <= 168 registers
+
+__global__ void __launch_bounds__(kFT, 2) psf_gen_fwd_kernel(const GenParams p) {
   extern __shared__ __align__(16) float gsm[];
   // all generators' weights -> shared memory, once per (persistent) CTA
-  for (int idx = threadIdx.x; idx < p.n_gen * kBlkFwd; idx += kTile) {
+  for (int idx = threadIdx.x; idx < p.n_gen * kBlkFwd; idx += kFT) {
     const int m = idx / kBlkFwd;
     int o = idx - m * kBlkFwd;
     const float *W1, *b1, *W2, *b2;
@@ -121,69 +149,89 @@ __global__ void __launch_bounds__(kTile, 2) psf_gen_fwd_kernel(const GenParams p
   }
   __syncthreads();
 
-  const long long ntiles = (p.rows + kTile - 1) / kTile;
+  const long long ntiles = (p.rows + 2 * kFT - 1) / (2 * kFT);
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long row = tile * kTile + threadIdx.x;
-    if (row >= p.rows) continue;
-    float2 x2[GE / 2];
-    {
-      const float4* xr = reinterpret_cast<const float4*>(p.x + row * GE);
+    long long row[2];
+    bool live[2];
+    float2 x2[2][GE / 2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      row[r] = tile * (2 * kFT) + r * kFT + threadIdx.x;
+      live[r] = row[r] < p.rows;
+      const float4* xr = reinterpret_cast<const float4*>(p.x + (live[r] ? row[r] : 0) * GE);
 #pragma unroll
       for (int i = 0; i < GE / 4; ++i) {
         const float4 v = __ldg(xr + i);
-        x2[2 * i] = make_float2(v.x, v.y);
-        x2[2 * i + 1] = make_float2(v.z, v.w);
+        x2[r][2 * i] = make_float2(v.x, v.y);
+        x2[r][2 * i + 1] = make_float2(v.z, v.w);
       }
     }
+    if (!live[0]) continue;
 #pragma unroll 1
     for (int m = 0; m < p.n_gen; ++m) {
       const float* w1 = gsm + m * kBlkFwd;
       const float* b1 = w1 + GH * GE;
       const float* w2t = b1 + GH;
       const float* b2 = w2t + GH * GLP;
-      float2 out2[GLP / 2];
+      float2 out2[2][GLP / 2];
 #pragma unroll
       for (int i = 0; i < GLP / 4; ++i) {
         const float4 b = lds4g(b2 + 4 * i);
-        out2[2 * i] = make_float2(b.x, b.y);
-        out2[2 * i + 1] = make_float2(b.z, b.w);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          out2[r][2 * i] = make_float2(b.x, b.y);
+          out2[r][2 * i + 1] = make_float2(b.z, b.w);
+        }
       }
-#pragma unroll
+#pragma unroll 1
       for (int hc = 0; hc < GH / 8; ++hc) {
-        float2 pre2[8];
+        float2 pre2[2][8];
 #pragma unroll
-        for (int h = 0; h < 8; ++h) pre2[h] = make_float2(0.f, 0.f);
+        for (int h = 0; h < 8; ++h) pre2[0][h] = pre2[1][h] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int e4 = 0; e4 < GE / 4; ++e4) {
 #pragma unroll
           for (int h = 0; h < 8; ++h) {
             const float4 w = lds4g(w1 + (hc * 8 + h) * GE + 4 * e4);
-            ffma2(pre2[h], make_float2(w.x, w.y), x2[2 * e4]);
-            ffma2(pre2[h], make_float2(w.z, w.w), x2[2 * e4 + 1]);
+            const float2 wa = make_float2(w.x, w.y), wc = make_float2(w.z, w.w);
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              ffma2(pre2[r][h], wa, x2[r][2 * e4]);
+              ffma2(pre2[r][h], wc, x2[r][2 * e4 + 1]);
+            }
           }
         }
 #pragma unroll
         for (int h = 0; h < 8; ++h) {
-          const float hid = gelu_f(pre2[h].x + pre2[h].y + b1[hc * 8 + h]);
-          const float2 hh = make_float2(hid, hid);
+          const float bias = b1[hc * 8 + h];
+          const float hid0 = gelu_f(pre2[0][h].x + pre2[0][h].y + bias);
+          const float hid1 = gelu_f(pre2[1][h].x + pre2[1][h].y + bias);
+          const float2 hh0 = make_float2(hid0, hid0), hh1 = make_float2(hid1, hid1);
 #pragma unroll
           for (int l4 = 0; l4 < GLP / 4; ++l4) {
             const float4 w = lds4g(w2t + (hc * 8 + h) * GLP + 4 * l4);
-            ffma2(out2[2 * l4], make_float2(w.x, w.y), hh);
-            ffma2(out2[2 * l4 + 1], make_float2(w.z, w.w), hh);
+            const float2 wa = make_float2(w.x, w.y), wc = make_float2(w.z, w.w);
+            ffma2(out2[0][2 * l4], wa, hh0);
+            ffma2(out2[0][2 * l4 + 1], wc, hh0);
+            ffma2(out2[1][2 * l4], wa, hh1);
+            ffma2(out2[1][2 * l4 + 1], wc, hh1);
           }
         }
       }
-      if (m < p.n_W) {
-        float* dst = p.Wt + (long long)m * p.sWf + row;
 #pragma unroll
-        for (int l = 0; l < GLP; ++l)
-          if (l < p.L) dst[(long long)l * p.sWt] = (l & 1) ? out2[l >> 1].y : out2[l >> 1].x;
-      } else {  // V0 row, natural order, row-major
-        float* dst = p.V + natural_row(p, row) * p.C;
+      for (int r = 0; r < 2; ++r) {
+        if (!live[r]) continue;
+        if (m < p.n_W) {
+          float* dst = p.Wt + (long long)m * p.sWf + row[r];
 #pragma unroll
-        for (int c = 0; c < GLP; ++c)
-          if (c < p.C) dst[c] = (c & 1) ? out2[c >> 1].y : out2[c >> 1].x;
+          for (int l = 0; l < GLP; ++l)
+            if (l < p.L) dst[(long long)l * p.sWt] = (l & 1) ? out2[r][l >> 1].y : out2[r][l >> 1].x;
+        } else {  // V0 row, natural order, row-major
+          float* dst = p.V + natural_row(p, row[r]) * p.C;
+#pragma unroll
+          for (int c = 0; c < GLP; ++c)
+            if (c < p.C) dst[c] = (c & 1) ? out2[r][c >> 1].y : out2[r][c >> 1].x;
+        }
       }
     }
   }
@@ -220,14 +268,26 @@ __global__ void __launch_bounds__(kTB, 3) psf_gen_bwd_kernel(const GenParams p) 
   float* dps = xs + kTB * XS;       // [kTB][XS]   dpre
   float* hs = dps + kTB * XS;       // [kTB][XS]   hidden activations
   float* dos = hs + kTB * XS;       // [kTB][DS]   dout (taps padded with zeros)
-  float* wb = dos + kTB * DS;       // weights of the current generator
-  const float* w1 = wb;
-  const float* b1 = wb + GH * GE;
-  const float* w2 = b1 + GH;          // [GLP][GH], rows >= L are zero
+  float* wb0 = dos + kTB * DS;      // weights of the current generator (filled by cp.async during the previous phase 2)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* wsc = p.ws + (long long)blockIdx.x * p.n_gen * kAccBlk;
   const long long ntiles = (p.rows + kTB - 1) / kTB;
+  // request generator m's weights: W1 1024 + b1 32 + W2 Lm*32 floats in 16 B pieces; the
+  // padding rows of W2 (taps >= Lm) are zeroed with plain stores
+  auto request_weights = [&](int m) {
+    const float *W1, *b1g, *W2, *b2g;
+    int Lm;
+    gen_ptrs(p, m, W1, b1g, W2, b2g, Lm);
+    float* dst = wb0;
+    const int n16 = (GH * GE + GH + Lm * GH) / 4;
+    for (int c = tid; c < n16; c += kTB) {
+      const int o = 4 * c;
+      const float* src = o < GH * GE ? W1 + o : (o < GH * GE + GH ? b1g + (o - GH * GE) : W2 + (o - GH * GE - GH));
+      cp_async16(dst + o, src);
+    }
+    for (int o = GH * GE + GH + Lm * GH + tid; o < kBlkBwd; o += kTB) dst[o] = 0.f;
+  };
 
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long row = tile * kTB + tid;
@@ -240,31 +300,19 @@ __global__ void __launch_bounds__(kTB, 3) psf_gen_bwd_kernel(const GenParams p) 
       dx2[2 * i] = make_float2(0.f, 0.f);
       dx2[2 * i + 1] = make_float2(0.f, 0.f);
     }
-    __syncthreads();  // phase 2 of the previous tile has finished reading xs
+    __syncthreads();  // phase 2 of the previous tile has finished reading xs and the weight buffers
 #pragma unroll
     for (int i = 0; i < GE / 4; ++i) *reinterpret_cast<float4*>(xs + tid * XS + 4 * i) = xin[i];
+    request_weights(0);
+    cp_async_commit();
 
     const long long nat = (live && p.n_gen > p.n_W) ? natural_row(p, row) : 0;
 #pragma unroll 1
     for (int m = 0; m < p.n_gen; ++m) {
-      __syncthreads();  // phase 2 of the previous generator is done with dps / hs / dos and the weights
-      {
-        const float *W1, *b1g, *W2, *b2g;
-        int Lm;
-        gen_ptrs(p, m, W1, b1g, W2, b2g, Lm);
-        for (int o = tid; o < kBlkBwd; o += kTB) {
-          float v;
-          if (o < GH * GE) {
-            v = W1[o];
-          } else if (o < GH * GE + GH) {
-            v = b1g[o - GH * GE];
-          } else {
-            const int q = o - GH * GE - GH, l = q / GH;
-            v = l < Lm ? W2[q] : 0.f;
-          }
-          wb[o] = v;
-        }
-      }
+      __syncthreads();  // phase 2 of the previous generator is done with dps / hs / dos
+      const float* w1 = wb0;
+      const float* b1 = w1 + GH * GE;
+      const float* w2 = b1 + GH;                       // [GLP][GH], rows >= Lm are zero
       float dout[GLP];
       {
         if (m < p.n_W) {
@@ -280,6 +328,7 @@ __global__ void __launch_bounds__(kTB, 3) psf_gen_bwd_kernel(const GenParams p) 
         for (int i = 0; i < GLP / 4; ++i)
           *reinterpret_cast<float4*>(dos + tid * DS + 4 * i) = make_float4(dout[4 * i], dout[4 * i + 1], dout[4 * i + 2], dout[4 * i + 3]);
       }
+      cp_async_wait<0>();  // this generator's weights (requested one phase 2 ago) have landed
       __syncthreads();
 
       // ---- phase 1: this thread's row (x comes back from the staged tile: it is not kept in registers
@@ -322,8 +371,8 @@ __global__ void __launch_bounds__(kTB, 3) psf_gen_bwd_kernel(const GenParams p) 
 #pragma unroll
         for (int h = 0; h < 8; ++h) {
           const float pre = pre2[h].x + pre2[h].y + b1[hc * 8 + h];
-          const float cdf = 0.5f * (1.f + erff(pre * 0.70710678118654752440f));
-          const float pdf = 0.39894228040143267794f * expf(-0.5f * pre * pre);
+          float cdf, pdf;
+          normal_cdf_pdf_fast(pre, cdf, pdf);
           hid[h] = pre * cdf;
           const float dhid = (h & 1) ? dh2[h >> 1].y : dh2[h >> 1].x;
           dpre[h] = dhid * (cdf + pre * pdf);
@@ -344,6 +393,8 @@ __global__ void __launch_bounds__(kTB, 3) psf_gen_bwd_kernel(const GenParams p) 
         *reinterpret_cast<float4*>(hs + tid * XS + hc * 8 + 4) = make_float4(hid[4], hid[5], hid[6], hid[7]);
       }
       __syncthreads();
+      if (m + 1 < p.n_gen) request_weights(m + 1);   // phase 2 does not read the weights: the next ones land meanwhile
+      cp_async_commit();
 
       float* acc_m = wsc + (long long)m * kAccBlk;
       // ---- phase 2a: dW1[h][e] += sum_rows dpre[row][h] * x[row][e]  (+ db1) -----------------
@@ -558,10 +609,10 @@ int psf_generators_fwd(const psf_gen_desc* d, const float* x, psf_mlp_params fs,
   if (d->rows == 0) return PSF_OK;
   p.Wt = W_out;
   p.V = V_out;
-  const long long ntiles = (d->rows + kTile - 1) / kTile;
+  const long long ntiles = (d->rows + 2 * kFT - 1) / (2 * kFT);
   long long grid = gen_grid(2);
   if (grid > ntiles) grid = ntiles;
-  psf_gen_fwd_kernel<<<(unsigned)grid, kTile, (size_t)p.n_gen * kBlkFwd * 4, (cudaStream_t)stream>>>(p);
+  psf_gen_fwd_kernel<<<(unsigned)grid, kFT, (size_t)p.n_gen * kBlkFwd * 4, (cudaStream_t)stream>>>(p);
   return (int)cudaGetLastError();
 }
 
@@ -576,6 +627,12 @@ int psf_generators_bwd(const psf_gen_desc* d, const float* x, psf_mlp_params fs,
   if (d->C > 0 && (dV_in == nullptr || dg.W1 == nullptr || dg.b1 == nullptr || dg.W2 == nullptr || dg.b2 == nullptr))
     return PSF_ERR_ARG;
   if (reinterpret_cast<uintptr_t>(dx) & 15) return PSF_ERR_ARG;
+  {  // the weights are staged with 16-byte cp.async copies
+    const void* ptrs[6] = {fs.W1, fs.b1, fs.W2, d->C > 0 ? g.W1 : nullptr, d->C > 0 ? g.b1 : nullptr,
+                           d->C > 0 ? g.W2 : nullptr};
+    for (int i = 0; i < 6; ++i)
+      if (reinterpret_cast<uintptr_t>(ptrs[i]) & 15) return PSF_ERR_ARG;
+  }
   if (workspace == nullptr || workspace_bytes < psf_generators_workspace_bytes(d->n_W)) return PSF_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   const long long ntiles = (d->rows + kTB - 1) / kTB;

@@ -21,11 +21,41 @@ E_FUSED, H_FUSED, OUT_MAX = 32, 32, 16
 
 
 class _Stats:
+    """Launch counter and optional CUDA-event timing of the generator kernels (used by bench.py)."""
+
     def __init__(self):
+        self.reset()
+
+    def reset(self, timing: bool = False):
         self.launches = 0
+        self.timing = timing
+        self.events = {"fwd": [], "bwd": []}
+
+    def mean_ms(self, kind: str) -> float:
+        ev = self.events[kind]
+        return sum(a.elapsed_time(b) for a, b in ev) / len(ev) if ev else float("nan")
 
 
 stats = _Stats()
+
+
+class _Timed:
+    def __init__(self, kind, launches):
+        self.kind, self.n = kind, launches
+
+    def __enter__(self):
+        stats.launches += self.n
+        if stats.timing:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if stats.timing:
+            self.b.record()
+            stats.events[self.kind].append((self.a, self.b))
+        return False
 
 
 def _mlp_ok(f: nn.Module) -> Optional[int]:
@@ -69,17 +99,18 @@ class _FusedGenerators(torch.autograd.Function):
         x, w1, b1, w2, b2 = (t.contiguous() for t in (x, w1, b1, w2, b2))
         has_g = gw1 is not None
         gs = tuple(t.contiguous() for t in (gw1, gb1, gw2, gb2)) if has_g else (None,) * 4
+        if has_g and any(t.data_ptr() % 16 for t in gs):      # the kernels stage weights in 16-byte pieces
+            gs = tuple(t.clone() for t in gs)
         rows = x.shape[0]
         n_W, L = w2.shape[0], w2.shape[1]
         Cg = gs[2].shape[0] if has_g else 0
         d = _capi.GenDesc(rows, n, n_W, E_FUSED, H_FUSED, L, L * rows, rows, int(interleave), Cg)
         out = torch.empty(n_W, L, rows, dtype=torch.float32, device=x.device)
         v0 = torch.empty(rows, Cg, dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
+        with torch.cuda.device(x.device), _Timed("fwd", 1):
             rc = lib.psf_generators_fwd(C.byref(d), x.data_ptr(), _ptrs((w1, b1, w2, b2)), _ptrs(gs), out.data_ptr(),
                                         v0.data_ptr() if has_g else None, torch.cuda.current_stream().cuda_stream)
         _capi.check(rc, "psf_generators_fwd")
-        stats.launches += 1
         ctx.save_for_backward(x, w1, b1, w2, b2, *(gs if has_g else ()))
         ctx.desc = d
         ctx.has_g = has_g
@@ -101,11 +132,12 @@ class _FusedGenerators(torch.autograd.Function):
         with torch.cuda.device(x.device):
             nbytes = int(lib.psf_generators_workspace_bytes(d.n_W))
             ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=x.device)
-            rc = lib.psf_generators_bwd(C.byref(d), x.data_ptr(), _ptrs((w1, b1, w2, b2)), _ptrs(gs), dout.data_ptr(),
-                                        dv0.data_ptr() if ctx.has_g else None, dx.data_ptr(), _ptrs(dfs), _ptrs(dgs),
-                                        ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+            with _Timed("bwd", 2):       # backward kernel + the fixed-order reduction of the per-CTA slices
+                rc = lib.psf_generators_bwd(C.byref(d), x.data_ptr(), _ptrs((w1, b1, w2, b2)), _ptrs(gs),
+                                            dout.data_ptr(), dv0.data_ptr() if ctx.has_g else None, dx.data_ptr(),
+                                            _ptrs(dfs), _ptrs(dgs), ws.data_ptr(), ws.numel(),
+                                            torch.cuda.current_stream().cuda_stream)
         _capi.check(rc, "psf_generators_bwd")
-        stats.launches += 2
         return (dx, None, None, *dfs, *dgs)
 
 
