@@ -57,6 +57,15 @@ namespace {
 #ifndef PSF2_PFW_BWD
 #define PSF2_PFW_BWD 3
 #endif
+// Backward residual accumulator (running sum of G_m over the factors, one quad set per thread and pass) in
+// TENSOR MEMORY instead of an L2-resident global buffer: every thread parks its 32 floats in 32 columns of its
+// own TMEM lane (tcgen05.st / tcgen05.ld, 32x32b shape), which takes the read-modify-write out of the LSU pipe,
+// out of L2 and - since the exchange buffers get written back - out of HBM.  Parity-green on B200, but MEASURED
+// SLOWER (backward 1.54 -> 2.2 ms at B = 132; already with the allocation alone and no TMEM traffic, see
+// profiles/r01_ablation.md), so the default stays 0 = L2-resident global buffer.
+#ifndef PSF2_TMEM_RACC
+#define PSF2_TMEM_RACC 0
+#endif
 // timing experiments only (results become wrong): 1 no W loads, 2 no dW stores, 4 no residual traffic,
 // 8 no V_{m-1} loads, 16 no remote operand loads, 32 no state stores, 64 no cluster barrier
 #ifndef PSF2_ABLATE
@@ -194,6 +203,38 @@ __device__ __forceinline__ void stcg4_keep(float* p, const float4& v, unsigned l
   asm volatile("st.global.cg.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
                "f"(v.w), "l"(pol)
                : "memory");
+}
+
+// ---- tensor memory as per-thread scratch (32 columns = one quad set of 8 channels) ------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst_u32, uint32_t ncols) {  // one warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst_u32), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // the same warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float4 (&v)[CT]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "f"(v[0].x), "f"(v[0].y), "f"(v[0].z), "f"(v[0].w), "f"(v[1].x), "f"(v[1].y), "f"(v[1].z), "f"(v[1].w),
+      "f"(v[2].x), "f"(v[2].y), "f"(v[2].z), "f"(v[2].w), "f"(v[3].x), "f"(v[3].y), "f"(v[3].z), "f"(v[3].w),
+      "f"(v[4].x), "f"(v[4].y), "f"(v[4].z), "f"(v[4].w), "f"(v[5].x), "f"(v[5].y), "f"(v[5].z), "f"(v[5].w),
+      "f"(v[6].x), "f"(v[6].y), "f"(v[6].z), "f"(v[6].w), "f"(v[7].x), "f"(v[7].y), "f"(v[7].z), "f"(v[7].w)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float4 (&v)[CT]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[0].z), "=f"(v[0].w), "=f"(v[1].x), "=f"(v[1].y), "=f"(v[1].z), "=f"(v[1].w),
+        "=f"(v[2].x), "=f"(v[2].y), "=f"(v[2].z), "=f"(v[2].w), "=f"(v[3].x), "=f"(v[3].y), "=f"(v[3].z), "=f"(v[3].w),
+        "=f"(v[4].x), "=f"(v[4].y), "=f"(v[4].z), "=f"(v[4].w), "=f"(v[5].x), "=f"(v[5].y), "=f"(v[5].z), "=f"(v[5].w),
+        "=f"(v[6].x), "=f"(v[6].y), "=f"(v[6].z), "=f"(v[6].w), "=f"(v[7].x), "=f"(v[7].y), "=f"(v[7].z), "=f"(v[7].w)
+      : "r"(taddr)
+      : "memory");
 }
 
 __device__ __forceinline__ void st_cs2(float* p, float a, float b) { __stcs(reinterpret_cast<float2*>(p), make_float2(a, b)); }
@@ -418,6 +459,21 @@ __global__ void __launch_bounds__(kNWB * 32, PSF2_MINB_BWD) psf_chain2_bwd_kerne
   uint32_t vparity = 0;
   bool cw_pending = false;
 
+#if PSF2_TMEM_RACC
+  // tensor memory for the residual accumulator: 32 columns per (warp group of 4, pass); power of two >= 32
+  constexpr uint32_t kRaccColsRaw = ((kNW + 3) / 4) * G::NPASS * 32;
+  constexpr uint32_t kRaccCols = kRaccColsRaw <= 32 ? 32 : kRaccColsRaw <= 64 ? 64 : kRaccColsRaw <= 128 ? 128 : kRaccColsRaw <= 256 ? 256 : 512;
+  static_assert(kRaccCols * PSF2_MINB_BWD <= 512, "tensor memory over-subscribed");
+  const uint32_t tslot = vbar + 16;  // shared-memory word that receives the TMEM base address
+  if (warp == 0) tmem_alloc(tslot, kRaccCols);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tbase;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tbase) : "r"(tslot) : "memory");
+  // this warp's lane quarter (warp % 4) and column block ((warp / 4) * NPASS + pass) * 32
+  const uint32_t twarp = tbase + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * (G::NPASS * 32u);
+#endif
   // exchange / residual buffers are per CLUSTER (reused sample after sample) so that they stay in L2
   const unsigned long long keep = make_evict_last_policy();
   float* gx0 = p.gx + (long long)cid * plane;
@@ -553,10 +609,17 @@ __global__ void __launch_bounds__(kNWB * 32, PSF2_MINB_BWD) psf_chain2_bwd_kerne
             tap(v, w, k, q * J + js);
           });
           auto issue_tail = [&]() {  // running sum of G_m over the factors (residual): this thread's own rows
+#if PSF2_TMEM_RACC
+            if (p.residual && !first && !(kAbl & 4)) {   // warp-uniform
+              tmem_wait_st();                            // the store of one factor ago (long complete)
+              tmem_ld32(twarp + (uint32_t)pp * 32u, R);  // lands behind the last group of local taps
+            }
+#else
             if (p.residual && !first && !(kAbl & 4)) {
 #pragma unroll
               for (int ch = 0; ch < CT; ++ch) R[ch] = ldcg4_keep(racc + ch * J + j, keep);
             }
+#endif
           };
           if constexpr (g == 0) {
             if (Q > 1 && cw_pending && !(kAbl & 64)) {
@@ -566,6 +629,23 @@ __global__ void __launch_bounds__(kNWB * 32, PSF2_MINB_BWD) psf_chain2_bwd_kerne
             issue_R(IC<0>{});
           } else if constexpr (g == G::NR + 1) {
             // residual: dV0 also receives G_m of every factor (V_m = W_m V_{m-1} + V_0)
+#if PSF2_TMEM_RACC
+            if (p.residual) {   // warp-uniform: the tensor-memory accesses are warp-collective
+              const uint32_t taddr = twarp + (uint32_t)pp * 32u;
+              if (!first && !(kAbl & 4)) tmem_wait_ld();
+#pragma unroll
+              for (int ch = 0; ch < CT; ++ch) {
+                const float4 own = lds4(state + ch * J + j);
+                if (first) R[ch] = own; else add4(R[ch], own);
+              }
+              if (!last) {
+                if (!(kAbl & 4)) tmem_st32(taddr, R);
+              } else {
+#pragma unroll
+                for (int ch = 0; ch < CT; ++ch) add4(acc[ch], R[ch]);
+              }
+            }
+#else
             if (p.residual) {
 #pragma unroll
               for (int ch = 0; ch < CT; ++ch) {
@@ -578,6 +658,7 @@ __global__ void __launch_bounds__(kNWB * 32, PSF2_MINB_BWD) psf_chain2_bwd_kerne
                 }
               }
             }
+#endif
           } else if constexpr (g == 1) {
             // ---- head: tap 3 on the previous quad Rq, then taps 0, 1, 2 on (Rq, own quad A) ----
             const float4 w3 = take_w(IC<G::idx_of(3)>{});
@@ -649,6 +730,12 @@ __global__ void __launch_bounds__(kNWB * 32, PSF2_MINB_BWD) psf_chain2_bwd_kerne
       cluster_wait();
     }
   }
+#if PSF2_TMEM_RACC
+  tmem_wait_st();
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, kRaccCols);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
