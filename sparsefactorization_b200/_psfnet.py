@@ -206,30 +206,90 @@ def generate_factors(fs: Sequence[MLPBlock], data: torch.Tensor, interleave: int
     raise RuntimeError("generator has no Linear layer")
 
 
-def generate_all(fs: Sequence[MLPBlock], g: MLPBlock, data: torch.Tensor, interleave: int = 1):
+def generate_all(fs: Sequence[MLPBlock], g: MLPBlock, data: torch.Tensor, interleave: int = 1,
+                 pre_interleaved: bool = False):
     """``(W, V0)``: every ``fs[m](data)`` and ``g(data)`` (psf.py:165, :175).  One fused kernel when the shapes
-    allow (W tap-major in the requested row order, V0 natural ``[B, n, C]``), else the GEMM routes."""
+    allow (W tap-major in the requested row order, V0 natural ``[B, n, C]``), else the GEMM routes.
+    ``pre_interleaved``: the rows of ``data`` already are in the quad-interleaved order (fused route only)."""
     B, n, E = data.shape
     if USE_FUSED_GENERATORS and _gen.fusable(fs, data, g):
         xp = data
-        if interleave > 1:
+        if interleave > 1 and not pre_interleaved:
             xp = data.view(B, n // (4 * interleave), interleave, 4, E).permute(0, 2, 1, 3, 4)
         wt, v0 = _gen.fused_generators(fs, xp.reshape(B * n, E), n, interleave, g)
         return wt.view(len(fs), wt.shape[1], B, n).permute(0, 2, 3, 1), v0.view(B, n, -1)
+    if pre_interleaved and interleave > 1:
+        raise RuntimeError("pre-interleaved rows need the fused generator kernels")
     return generate_factors(fs, data, interleave), g(data)
+
+
+class _SkinnyLinear(torch.autograd.Function):
+    """``x @ W^T + b`` for a very narrow input (init_linear = Linear(2, E), psf.py:136-141) over millions of rows.
+    Forward is addmm; the weight gradient ``dy^T x`` (E x 2 output, K = B*n) is evaluated split-K as a batched GEMM —
+    autograd's single GEMM picks a 128x32 SIMT tile for it (0.8 ms of a 16 ms step at cfg2)."""
+
+    KC = 4096
+
+    @staticmethod
+    def forward(ctx, x2d, w, b):
+        ctx.save_for_backward(x2d, w)
+        return torch.addmm(b, x2d, w.t())
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        x2d, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        rows = x2d.shape[0]
+        dx = dy @ w if ctx.needs_input_grad[0] else None
+        kc = _SkinnyLinear.KC
+        while rows % kc:
+            kc //= 2
+        S = rows // kc
+        part = torch.bmm(dy.view(S, kc, -1).transpose(1, 2), x2d.reshape(S, kc, -1))      # [S, E, in]
+        return dx, part.sum(0), dy.sum(0)
+
+
+def skinny_linear(lin: nn.Linear, x: torch.Tensor) -> torch.Tensor:
+    """``lin(x)`` through :class:`_SkinnyLinear` when the input is narrow, on CUDA and batched; else ``lin(x)``."""
+    if lin.in_features <= 4 and x.is_cuda and lin.bias is not None and x.dim() >= 2:
+        y = _SkinnyLinear.apply(x.reshape(-1, lin.in_features), lin.weight, lin.bias)
+        return y.view(*x.shape[:-1], lin.out_features)
+    return lin(x)
 
 
 class PSFChainMixin:
     """forward() tail shared by the variants: W generation + fused chain (psf.py:165-188)."""
 
-    def _chain_from_data(self, data: torch.Tensor, v_dropout=None) -> torch.Tensor:
-        """``V = g(data)`` (+ the LRA variants' dropout2), ``W_m = fs[m](data)``, then the chain."""
+    def _early_interleave(self, raw: torch.Tensor) -> int:
+        """Row interleave Q (> 1) if this batch will run the fused generators + gen-2 chain: the caller may then
+        permute the rows of the RAW input (tokens / 2 floats per row) instead of the embedded rows.  1 otherwise."""
+        if not (USE_FUSED_GENERATORS and raw.is_cuda and self.embedding_size == _gen.E_FUSED
+                and _gen.fusable_modules(self.fs, self.g)):
+            return 1
+        L = self.fs[0].network[-1].out_features
+        return preferred_interleave(len(self.fs), raw.shape[0], self.n_vec, L, self.g.network[-1].out_features)
+
+    def _row_perm(self, Q: int, device) -> torch.Tensor:
+        key = (Q, str(device))
+        cache = self.__dict__.setdefault("_perm_cache", {})
+        if key not in cache:
+            cache[key] = row_permutation(self.n_vec, Q, device)
+        return cache[key]
+
+    def _chain_from_data(self, data: torch.Tensor, v_dropout=None, pre_interleaved: int = 1) -> torch.Tensor:
+        """``V = g(data)`` (+ the LRA variants' dropout2), ``W_m = fs[m](data)``, then the chain.
+        ``pre_interleaved = Q > 1``: the rows of ``data`` are already quad-interleaved (see _early_interleave)."""
         n_W, (B, n, _) = len(self.fs), data.shape
         L = self.fs[0].network[-1].out_features
         Cv = self.g.network[-1].out_features
         homog = _same_structure(self.fs)
         Q = preferred_interleave(n_W, B, n, L, Cv) if data.dtype == torch.float32 and homog else 1
-        if homog:
+        if pre_interleaved > 1:
+            if pre_interleaved != Q or data.dtype != torch.float32:
+                raise RuntimeError("rows were pre-interleaved for a kernel that is not going to run")
+            W, V = generate_all(self.fs, self.g, data, Q, pre_interleaved=True)
+        elif homog:
             W, V = generate_all(self.fs, self.g, data, Q)
         else:
             W, V = generate_factors(self.fs, data, 1), self.g(data)

@@ -75,14 +75,21 @@ def _mlp_ok(f: nn.Module) -> Optional[int]:
     return b.out_features
 
 
-def fusable(fs: Sequence[nn.Module], data: torch.Tensor, g: Optional[nn.Module] = None) -> bool:
-    """True when every generator (and ``g`` if given) has the fused kernel's shape, on fp32 CUDA data."""
-    if not (data.is_cuda and data.dtype == torch.float32 and data.shape[-1] == E_FUSED and len(fs) >= 1):
+def fusable_modules(fs: Sequence[nn.Module], g: Optional[nn.Module] = None) -> bool:
+    """True when every generator (and ``g`` if given) has the fused kernel's shape (fp32 CUDA parameters)."""
+    if len(fs) < 1:
         return False
     outs = {_mlp_ok(f) for f in fs}
     if len(outs) != 1 or None in outs:
         return False
     return g is None or _mlp_ok(g) is not None
+
+
+def fusable(fs: Sequence[nn.Module], data: torch.Tensor, g: Optional[nn.Module] = None) -> bool:
+    """``fusable_modules`` and fp32 CUDA data of width 32."""
+    if not (data.is_cuda and data.dtype == torch.float32 and data.shape[-1] == E_FUSED):
+        return False
+    return fusable_modules(fs, g)
 
 
 def _ptrs(ts):

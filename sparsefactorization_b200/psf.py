@@ -10,7 +10,8 @@ from __future__ import annotations
 import torch
 from torch import nn
 
-from ._psfnet import MakeMLP, MLPBlock, PSFChainMixin, chord_mask, get_chord_indices_assym  # noqa: F401
+from ._psfnet import (MakeMLP, MLPBlock, PSFChainMixin, chord_mask, get_chord_indices_assym,  # noqa: F401
+                      skinny_linear)
 
 __all__ = ["get_chord_indices_assym", "chord_mask", "MakeMLP", "MLPBlock", "PSFNet"]
 
@@ -62,12 +63,18 @@ class PSFNet(PSFChainMixin, nn.Module):
         self._make_indices()     # attribute ``chord_indicies`` (sic), int64 [2, n_vec*n_links]; not a buffer
 
     def forward(self, data):
+        # the gen-2 chain kernel wants W with quad-interleaved rows: permute the raw input rows (a few bytes
+        # each) rather than the embedded ones; everything up to the generators is row-wise
+        Q = self._early_interleave(data)
+        perm = self._row_perm(Q, data.device) if Q > 1 else None
+        if perm is not None:
+            data = data.index_select(1, perm)
         if self.problem == 'order':
             data = self.embedding(data).squeeze(-2)
         if self.add_init_linear_layer:
-            data = self.init_linear(data)
+            data = skinny_linear(self.init_linear, data)
         if self.use_pos_embedding:
-            positions = torch.arange(0, self.n_vec, device=data.device).expand(data.size(0), self.n_vec)
-            data = data + self.pos_embedding(positions)
-        V = self._chain_from_data(data)         # V = g(data), all n_W factors (+ residual V_0 after each)
+            positions = perm if perm is not None else torch.arange(0, self.n_vec, device=data.device)
+            data = data + self.pos_embedding(positions.expand(data.size(0), self.n_vec))
+        V = self._chain_from_data(data, pre_interleaved=Q)   # V = g(data), all n_W factors (+ residual V_0 after each)
         return self.final(V.reshape(V.size(0), -1))

@@ -135,28 +135,39 @@ def test_gen2_shift_factors_are_a_rotation():
         assert torch.equal(out, torch.roll(V0, -shift, dims=1)), start
 
 
-def test_psfnet_large_n_uses_gen2_and_matches_oracle_module():
-    """Module level at n = 4096 (Q = 2): generators emit W quad-interleaved, logits and gradients must match
-    the oracle's restatement of the reference module (SyntheticExperiments/psf.py) on the same weights."""
-    from sparsefactorization_b200 import chain
+@pytest.mark.parametrize("problem", ["adding", "order"])
+def test_psfnet_large_n_uses_gen2_and_matches_oracle_module(problem):
+    """Module level at n = 4096 (Q = 2): the raw input rows are permuted, the fused generators emit W
+    quad-interleaved and V0 in natural order; logits and gradients must match the oracle's restatement of the
+    reference module (SyntheticExperiments/psf.py) on the same weights.  `order` adds the token and position
+    embeddings (psf.py:151-162)."""
+    from sparsefactorization_b200 import chain, generators
     from sparsefactorization_b200.psf import PSFNet
     n, n_W, B = 4096, 12, 2
-    kw = dict(vocab_size=1, add_init_linear_layer=True, embedding_size=32, n_vec=n, n_W=n_W, Ws=[32, "GELU"],
-              V=[32, "GELU"], n_channels_V=8, n_class=1, pooling_type="FLATTEN", head=["linear"],
-              use_residuals=True, use_pos_embedding=False, problem="adding")
+    adding = problem == "adding"
+    kw = dict(vocab_size=1 if adding else 6, add_init_linear_layer=adding, embedding_size=32, n_vec=n, n_W=n_W,
+              Ws=[32, "GELU"], V=[32, "GELU"], n_channels_V=8, n_class=1 if adding else 4, pooling_type="FLATTEN",
+              head=["linear"], use_residuals=True, use_pos_embedding=not adding, problem=problem)
     torch.manual_seed(5)
     ref = oracle.OraclePSFNet("synthetic", use_cuda=False, **kw)
     net = PSFNet(use_cuda=True, **kw)
     net.load_state_dict(ref.state_dict(), strict=True)
     net = net.cuda()
     g = torch.Generator().manual_seed(6)
-    X = torch.stack([1 - 2 * torch.rand(B, n, generator=g), (torch.rand(B, n, generator=g) < 0.001).float()], -1)
-    Y = torch.rand(B, generator=g)
+    if adding:
+        X = torch.stack([1 - 2 * torch.rand(B, n, generator=g), (torch.rand(B, n, generator=g) < 0.001).float()], -1)
+        Y = torch.rand(B, generator=g)
+        loss = lambda out, y: torch.nn.functional.mse_loss(out.squeeze(), y)
+    else:
+        X = torch.randint(0, 6, (B, n, 1), generator=g)
+        Y = torch.randint(0, 4, (B,), generator=g)
+        loss = torch.nn.functional.cross_entropy
     want = ref(X)
-    torch.nn.functional.mse_loss(want.squeeze(), Y).backward()
+    loss(want, Y).backward()
+    before = generators.stats.launches
     got = net(X.cuda())
-    assert chain.last_path_used == "fused"
-    torch.nn.functional.mse_loss(got.squeeze(), Y.cuda()).backward()
+    assert chain.last_path_used == "fused" and generators.stats.launches == before + 1
+    loss(got, Y.cuda()).backward()
     np.testing.assert_allclose(got.detach().cpu().numpy(), want.detach().numpy(), rtol=1e-4, atol=2e-6)
     ref_grads = dict(ref.named_parameters())
     for k, p in net.named_parameters():
