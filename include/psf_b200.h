@@ -154,8 +154,8 @@ int psf_chain_fused_generation(const psf_chain_desc* d);
  *   b1 [.,32], W2 [.,out,32], b2 [.,out]; `fs` tensors are stacked over the n_W generators, `g` is single.
  *   W_out / dW_in: element (m, l, row) at m*stride_factor + l*stride_tap + row (the chain's tap-major
  *   layout, row order = that of x).  V_out / dV_in: [rows, C] row-major in NATURAL row order (what the chain
- *   takes as V0).  C = 0: no V generator (g pointers ignored).  The backward pass recomputes the hidden
- *   activations and needs psf_generators_workspace_bytes(n_W) bytes of device workspace (overwritten). */
+ *   takes as V0).  C = 0: no V generator (g pointers ignored).  The backward pass needs
+ *   psf_generators_workspace_bytes(n_W) bytes of device workspace (overwritten). */
 typedef struct {
   int64_t rows;                       /* B*n                                                   */
   int64_t n;                          /* rows per sample (used when interleave > 1 or C > 0)   */
@@ -168,11 +168,13 @@ typedef struct { const float *W1, *b1, *W2, *b2; } psf_mlp_params;
 typedef struct { float *W1, *b1, *W2, *b2; } psf_mlp_grads;
 
 size_t psf_generators_workspace_bytes(int n_W);
+/* pre_save (may be NULL): [n_W + (C > 0)][32][rows] floats receiving the pre-activations for the backward pass. */
 int psf_generators_fwd(const psf_gen_desc* d, const float* x, psf_mlp_params fs, psf_mlp_params g, float* W_out,
-                       float* V_out, psf_stream_t stream);
+                       float* V_out, float* pre_save, psf_stream_t stream);
+/* pre_saved (may be NULL): what the forward pass wrote; NULL = recompute the pre-activations from x. */
 int psf_generators_bwd(const psf_gen_desc* d, const float* x, psf_mlp_params fs, psf_mlp_params g,
-                       const float* dW_in, const float* dV_in, float* dx, psf_mlp_grads dfs, psf_mlp_grads dg,
-                       void* workspace, size_t workspace_bytes, psf_stream_t stream);
+                       const float* dW_in, const float* dV_in, const float* pre_saved, float* dx, psf_mlp_grads dfs,
+                       psf_mlp_grads dg, void* workspace, size_t workspace_bytes, psf_stream_t stream);
 
 /* Launch geometry the fused path would use for this problem (for benches / docs):
  * cluster size, rows per CTA, threads per CTA, dynamic SMEM bytes, resident clusters.

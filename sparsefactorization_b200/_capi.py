@@ -65,9 +65,9 @@ _SIGNATURES = {
     "psf_chain_fused_generation": (C.c_int, [C.POINTER(ChainDesc)]),
     "psf_generators_workspace_bytes": (C.c_size_t, [C.c_int]),
     "psf_generators_fwd": (C.c_int, [C.POINTER(GenDesc), C.c_void_p, MlpPtrs, MlpPtrs, C.c_void_p, C.c_void_p,
-                                     C.c_void_p]),
+                                     C.c_void_p, C.c_void_p]),
     "psf_generators_bwd": (C.c_int, [C.POINTER(GenDesc), C.c_void_p, MlpPtrs, MlpPtrs, C.c_void_p, C.c_void_p,
-                                     C.c_void_p, MlpPtrs, MlpPtrs, C.c_void_p, C.c_size_t, C.c_void_p]),
+                                     C.c_void_p, C.c_void_p, MlpPtrs, MlpPtrs, C.c_void_p, C.c_size_t, C.c_void_p]),
     "psf_chain_fused_plan": (C.c_int, [C.POINTER(ChainDesc), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                        C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
 }

@@ -8,16 +8,17 @@
 //             reads from shared memory, hidden activations never leave registers.  HBM traffic is the
 //             compulsory 128 B in + 4*L*n_W B out per row (the cuBLAS route wrote and re-read three
 //             [rows, n_W*32] buffers).
-//   backward: dW [n_W][L][rows] -> dx [rows,32], dW1, db1, dW2, db2.  The hidden activations are
-//             RECOMPUTED from x (1 KFMA per row and generator; saving them would be 3.9 GB at the
-//             headline shape).  Per 128-row tile and generator (128 threads, three CTAs per SM so that
+//   backward: dW [n_W][L][rows] -> dx [rows,32], dW1, db1, dW2, db2.  The pre-activations come from the
+//             forward pass when it was asked to save them ([n_gen][32][rows], 4.2 GB at the headline shape,
+//             written and read with coalesced streaming accesses behind compute-bound kernels) or are
+//             RECOMPUTED from x (1 KFMA + 256 broadcast quads per row and generator).  Per 128-row tile and generator (128 threads, three CTAs per SM so that
 //             the phases of different tiles overlap):
 //               phase 1 (thread = row): pre, gelu, gelu', dhid = dout W2, dpre, dx += dpre W1;
 //                        dpre / hid / dout staged in shared memory,
 //               phase 2 (thread = 8x8 output tile x one row group): dW1 += dpre^T x, dW2 += dout^T hid
 //                        as register-tiled outer products over the tile's rows, reduced across row
 //                        groups with a shuffle reduce-scatter, accumulated into a per-CTA slice of a
-//                        global workspace (plain read-modify-write by the owning thread: deterministic).
+//                        global workspace (fire-and-forget red.add by the one owning thread: deterministic).
 //             A second tiny kernel sums the per-CTA slices in a fixed order.
 #include "psf_internal.cuh"
 
@@ -63,6 +64,14 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
                : "memory");
 }
+// fire-and-forget vector add to global memory (no read latency on the issuing thread).  Every accumulator element
+// is only ever touched by one thread, in program order, so the sums stay deterministic.
+__device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add1(float* p, float a) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -83,6 +92,7 @@ struct GenParams {
   float* V;         // fwd: V0 [rows][C] in NATURAL row order;  bwd: dV0 (read)
   float* dx;        // bwd: [rows][32]
   float* ws;        // bwd: [grid][n_gen][kAccBlk]
+  float* pre;       // optional [n_gen][32][rows]: pre-activations saved by the forward pass for the backward pass
   long long rows, sWf, sWt;
   int n_W, L;
   int n_gen;        // n_W + (g present)
@@ -204,8 +214,14 @@ __global__ void __launch_bounds__(kFT, 2) psf_gen_fwd_kernel(const GenParams p) 
 #pragma unroll
         for (int h = 0; h < 8; ++h) {
           const float bias = b1[hc * 8 + h];
-          const float hid0 = gelu_f(pre2[0][h].x + pre2[0][h].y + bias);
-          const float hid1 = gelu_f(pre2[1][h].x + pre2[1][h].y + bias);
+          const float pre0 = pre2[0][h].x + pre2[0][h].y + bias, pre1 = pre2[1][h].x + pre2[1][h].y + bias;
+          if (p.pre != nullptr) {  // coalesced: consecutive lanes are consecutive rows
+            float* ps = p.pre + (long long)(m * GH + hc * 8 + h) * p.rows;
+            __stcs(ps + row[0], pre0);
+            if (live[1]) __stcs(ps + row[1], pre1);
+          }
+          const float hid0 = gelu_f(pre0);
+          const float hid1 = gelu_f(pre1);
           const float2 hh0 = make_float2(hid0, hid0), hh1 = make_float2(hid1, hid1);
 #pragma unroll
           for (int l4 = 0; l4 < GLP / 4; ++l4) {
@@ -262,6 +278,7 @@ __device__ __forceinline__ void rs_step(float* v, int M, bool hi) {
   }
 }
 
+template <bool kSaved>
 __global__ void __launch_bounds__(kTB, 3) psf_gen_bwd_kernel(const GenParams p) {
   extern __shared__ __align__(16) float gsm[];
   float* xs = gsm;                    // [kTB][XS]   x rows of the tile
@@ -307,6 +324,21 @@ __global__ void __launch_bounds__(kTB, 3) psf_gen_bwd_kernel(const GenParams p) 
     cp_async_commit();
 
     const long long nat = (live && p.n_gen > p.n_W) ? natural_row(p, row) : 0;
+    // incoming gradient of generator mm for this thread's row (streamed from HBM: fetched one generator ahead,
+    // behind phase 2, so that its latency is not on the tile's critical path)
+    auto load_dout = [&](int mm, float (&d)[GLP]) {
+      if (mm < p.n_W) {
+        const float* src = p.Wt + (long long)mm * p.sWf + row;
+#pragma unroll
+        for (int l = 0; l < GLP; ++l) d[l] = (live && l < p.L) ? __ldcs(src + (long long)l * p.sWt) : 0.f;
+      } else {
+        const float* src = p.V + nat * p.C;
+#pragma unroll
+        for (int c = 0; c < GLP; ++c) d[c] = (live && c < p.C) ? __ldcs(src + c) : 0.f;
+      }
+    };
+    float dnext[GLP];
+    load_dout(0, dnext);
 #pragma unroll 1
     for (int m = 0; m < p.n_gen; ++m) {
       __syncthreads();  // phase 2 of the previous generator is done with dps / hs / dos
@@ -315,15 +347,8 @@ __global__ void __launch_bounds__(kTB, 3) psf_gen_bwd_kernel(const GenParams p) 
       const float* w2 = b1 + GH;                       // [GLP][GH], rows >= Lm are zero
       float dout[GLP];
       {
-        if (m < p.n_W) {
-          const float* src = p.Wt + (long long)m * p.sWf + row;
 #pragma unroll
-          for (int l = 0; l < GLP; ++l) dout[l] = (live && l < p.L) ? __ldcs(src + (long long)l * p.sWt) : 0.f;
-        } else {
-          const float* src = p.V + nat * p.C;
-#pragma unroll
-          for (int c = 0; c < GLP; ++c) dout[c] = (live && c < p.C) ? __ldcs(src + c) : 0.f;
-        }
+        for (int l = 0; l < GLP; ++l) dout[l] = dnext[l];
 #pragma unroll
         for (int i = 0; i < GLP / 4; ++i)
           *reinterpret_cast<float4*>(dos + tid * DS + 4 * i) = make_float4(dout[4 * i], dout[4 * i + 1], dout[4 * i + 2], dout[4 * i + 3]);
@@ -334,24 +359,33 @@ __global__ void __launch_bounds__(kTB, 3) psf_gen_bwd_kernel(const GenParams p) 
       // ---- phase 1: this thread's row (x comes back from the staged tile: it is not kept in registers
       //      across phase 2, whose 8 x 8 accumulator tile needs them) ------------------------------
       float2 x2[GE / 2];
+      if constexpr (!kSaved) {
 #pragma unroll
-      for (int i = 0; i < GE / 4; ++i) {
-        const float4 v = lds4g(xs + tid * XS + 4 * i);
-        x2[2 * i] = make_float2(v.x, v.y);
-        x2[2 * i + 1] = make_float2(v.z, v.w);
+        for (int i = 0; i < GE / 4; ++i) {
+          const float4 v = lds4g(xs + tid * XS + 4 * i);
+          x2[2 * i] = make_float2(v.x, v.y);
+          x2[2 * i + 1] = make_float2(v.z, v.w);
+        }
       }
 #pragma unroll 1
       for (int hc = 0; hc < GH / 8; ++hc) {
         float2 pre2[8];
+        float prs[8];
+        if constexpr (kSaved) {  // pre-activations saved by the forward pass: coalesced loads, used after dhid
+          const float* ps = p.pre + (long long)(m * GH + hc * 8) * p.rows + (live ? row : 0);
 #pragma unroll
-        for (int h = 0; h < 8; ++h) pre2[h] = make_float2(0.f, 0.f);
+          for (int h = 0; h < 8; ++h) prs[h] = __ldcs(ps + (long long)h * p.rows);
+        } else {
 #pragma unroll
-        for (int e4 = 0; e4 < GE / 4; ++e4) {
+          for (int h = 0; h < 8; ++h) pre2[h] = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int h = 0; h < 8; ++h) {
-            const float4 w = lds4g(w1 + (hc * 8 + h) * GE + 4 * e4);
-            ffma2(pre2[h], make_float2(w.x, w.y), x2[2 * e4]);
-            ffma2(pre2[h], make_float2(w.z, w.w), x2[2 * e4 + 1]);
+          for (int e4 = 0; e4 < GE / 4; ++e4) {
+#pragma unroll
+            for (int h = 0; h < 8; ++h) {
+              const float4 w = lds4g(w1 + (hc * 8 + h) * GE + 4 * e4);
+              ffma2(pre2[h], make_float2(w.x, w.y), x2[2 * e4]);
+              ffma2(pre2[h], make_float2(w.z, w.w), x2[2 * e4 + 1]);
+            }
           }
         }
         float2 dh2[4];
@@ -370,7 +404,7 @@ __global__ void __launch_bounds__(kTB, 3) psf_gen_bwd_kernel(const GenParams p) 
         float hid[8], dpre[8];
 #pragma unroll
         for (int h = 0; h < 8; ++h) {
-          const float pre = pre2[h].x + pre2[h].y + b1[hc * 8 + h];
+          const float pre = kSaved ? prs[h] : pre2[h].x + pre2[h].y + b1[hc * 8 + h];
           float cdf, pdf;
           normal_cdf_pdf_fast(pre, cdf, pdf);
           hid[h] = pre * cdf;
@@ -393,7 +427,10 @@ __global__ void __launch_bounds__(kTB, 3) psf_gen_bwd_kernel(const GenParams p) 
         *reinterpret_cast<float4*>(hs + tid * XS + hc * 8 + 4) = make_float4(hid[4], hid[5], hid[6], hid[7]);
       }
       __syncthreads();
-      if (m + 1 < p.n_gen) request_weights(m + 1);   // phase 2 does not read the weights: the next ones land meanwhile
+      if (m + 1 < p.n_gen) {   // phase 2 reads neither the weights nor dout: the next generator's land meanwhile
+        request_weights(m + 1);
+        load_dout(m + 1, dnext);
+      }
       cp_async_commit();
 
       float* acc_m = wsc + (long long)m * kAccBlk;
@@ -428,23 +465,14 @@ __global__ void __launch_bounds__(kTB, 3) psf_gen_bwd_kernel(const GenParams p) 
         rs_step2<8>(v, 2, lane & 2);
         rs_step2<4>(v, 1, lane & 1);
         const int i = ((lane & 4) ? 4 : 0) + ((lane & 2) ? 2 : 0) + (lane & 1);   // tile row this lane ends up owning
-        float4* dst = reinterpret_cast<float4*>(acc_m + (hb * 8 + i) * GE + eb * 8);
-        float4 c0 = dst[0], c1 = dst[1];
-        c0.x += v[0].x;
-        c0.y += v[0].y;
-        c0.z += v[1].x;
-        c0.w += v[1].y;
-        c1.x += v[2].x;
-        c1.y += v[2].y;
-        c1.z += v[3].x;
-        c1.w += v[3].y;
-        dst[0] = c0;
-        dst[1] = c1;
+        float* dst = acc_m + (hb * 8 + i) * GE + eb * 8;
+        red_add4(dst, v[0].x, v[0].y, v[1].x, v[1].y);
+        red_add4(dst + 4, v[2].x, v[2].y, v[3].x, v[3].y);
         // bias gradient: every lane group holds the column sums of dpre; the eb == 0 tiles write them
         rs_step<4>(db, 4, lane & 4);
         rs_step<2>(db, 2, lane & 2);
         rs_step<1>(db, 1, lane & 1);
-        if (eb == 0) acc_m[GH * GE + hb * 8 + i] += db[0];
+        if (eb == 0) red_add1(acc_m + GH * GE + hb * 8 + i, db[0]);
       }
       // ---- phase 2b: dW2[l][h] += sum_rows dout[row][l] * hid[row][h]  (+ db2) ----------------
       {
@@ -478,20 +506,14 @@ __global__ void __launch_bounds__(kTB, 3) psf_gen_bwd_kernel(const GenParams p) 
         rs_step2<4>(v, 2, lane & 2);
         rs_step2<2>(v, 1, lane & 1);
         const int o = ((lane & 8) ? 32 : 0) + ((lane & 4) ? 16 : 0) + ((lane & 2) ? 8 : 0) + ((lane & 1) ? 4 : 0);
-        float4* dst = reinterpret_cast<float4*>(acc_m + GH * GE + GH + (lb * 8 + (o >> 3)) * GH + hb * 8 + (o & 7));
-        float4 cur = *dst;
-        cur.x += v[0].x;
-        cur.y += v[0].y;
-        cur.z += v[1].x;
-        cur.w += v[1].y;
-        *dst = cur;
+        red_add4(acc_m + GH * GE + GH + (lb * 8 + (o >> 3)) * GH + hb * 8 + (o & 7), v[0].x, v[0].y, v[1].x, v[1].y);
         rs_step<4>(db, 8, lane & 8);
         rs_step<2>(db, 4, lane & 4);
         rs_step<1>(db, 2, lane & 2);
         db[0] += __shfl_xor_sync(0xffffffffu, db[0], 1);
         if (hb == 0 && !(lane & 1)) {
           const int l = lb * 8 + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
-          acc_m[GH * GE + GH + GLP * GH + l] += db[0];
+          red_add1(acc_m + GH * GE + GH + GLP * GH + l, db[0]);
         }
       }
     }
@@ -550,7 +572,8 @@ int gen_check(int64_t rows, int n_W, int E, int H, int L) {
   if (n_W * kBlkFwd * 4 > 110 * 1024) return PSF_ERR_UNSUPPORTED;  // forward keeps every generator's weights resident
   if (!g_gen_attr) {
     if (cudaFuncSetAttribute(psf_gen_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(psf_gen_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBwd) != cudaSuccess) {
+        cudaFuncSetAttribute(psf_gen_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBwd) != cudaSuccess ||
+        cudaFuncSetAttribute(psf_gen_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBwd) != cudaSuccess) {
       cudaGetLastError();
       return PSF_ERR_UNSUPPORTED;
     }
@@ -601,7 +624,7 @@ static int gen_fill(GenParams& p, const psf_gen_desc* d, const float* x, const p
 }
 
 int psf_generators_fwd(const psf_gen_desc* d, const float* x, psf_mlp_params fs, psf_mlp_params g, float* W_out,
-                       float* V_out, psf_stream_t stream) {
+                       float* V_out, float* pre_save, psf_stream_t stream) {
   GenParams p = {};
   int rc = gen_fill(p, d, x, fs, g);
   if (rc) return rc;
@@ -609,6 +632,7 @@ int psf_generators_fwd(const psf_gen_desc* d, const float* x, psf_mlp_params fs,
   if (d->rows == 0) return PSF_OK;
   p.Wt = W_out;
   p.V = V_out;
+  p.pre = pre_save;
   const long long ntiles = (d->rows + 2 * kFT - 1) / (2 * kFT);
   long long grid = gen_grid(2);
   if (grid > ntiles) grid = ntiles;
@@ -617,8 +641,8 @@ int psf_generators_fwd(const psf_gen_desc* d, const float* x, psf_mlp_params fs,
 }
 
 int psf_generators_bwd(const psf_gen_desc* d, const float* x, psf_mlp_params fs, psf_mlp_params g, const float* dW_in,
-                       const float* dV_in, float* dx, psf_mlp_grads dfs, psf_mlp_grads dg, void* workspace,
-                       size_t workspace_bytes, psf_stream_t stream) {
+                       const float* dV_in, const float* pre_saved, float* dx, psf_mlp_grads dfs, psf_mlp_grads dg,
+                       void* workspace, size_t workspace_bytes, psf_stream_t stream) {
   GenParams p = {};
   int rc = gen_fill(p, d, x, fs, g);
   if (rc) return rc;
@@ -644,8 +668,12 @@ int psf_generators_bwd(const psf_gen_desc* d, const float* x, psf_mlp_params fs,
   p.V = const_cast<float*>(dV_in);
   p.dx = dx;
   p.ws = (float*)workspace;
+  p.pre = const_cast<float*>(pre_saved);
   if (d->rows > 0) {
-    psf_gen_bwd_kernel<<<(unsigned)grid, kTB, kSmemBwd, st>>>(p);
+    if (pre_saved != nullptr)
+      psf_gen_bwd_kernel<true><<<(unsigned)grid, kTB, kSmemBwd, st>>>(p);
+    else
+      psf_gen_bwd_kernel<false><<<(unsigned)grid, kTB, kSmemBwd, st>>>(p);
     PSF_CUDA_TRY(cudaGetLastError());
   }
   GenGrads gg = {dfs.W1, dfs.b1, dfs.W2, dfs.b2, dg.W1, dg.b1, dg.W2, dg.b2};

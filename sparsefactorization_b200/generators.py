@@ -18,6 +18,8 @@ from torch import nn
 from . import _capi
 
 E_FUSED, H_FUSED, OUT_MAX = 32, 32, 16
+SAVE_PREACTIVATIONS = False   # True: the forward pass saves them ([n_gen, 32, rows], 4.2 GB at the headline shape) and
+                              # the backward pass reads them back instead of recomputing; measured no faster
 
 
 class _Stats:
@@ -114,11 +116,17 @@ class _FusedGenerators(torch.autograd.Function):
         d = _capi.GenDesc(rows, n, n_W, E_FUSED, H_FUSED, L, L * rows, rows, int(interleave), Cg)
         out = torch.empty(n_W, L, rows, dtype=torch.float32, device=x.device)
         v0 = torch.empty(rows, Cg, dtype=torch.float32, device=x.device)
+        # pre-activations for the backward pass (saves it the recompute): only when a gradient will be asked for
+        pre = None
+        if SAVE_PREACTIVATIONS and any(ctx.needs_input_grad):
+            pre = torch.empty(n_W + (1 if has_g else 0), H_FUSED, rows, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device), _Timed("fwd", 1):
             rc = lib.psf_generators_fwd(C.byref(d), x.data_ptr(), _ptrs((w1, b1, w2, b2)), _ptrs(gs), out.data_ptr(),
-                                        v0.data_ptr() if has_g else None, torch.cuda.current_stream().cuda_stream)
+                                        v0.data_ptr() if has_g else None, pre.data_ptr() if pre is not None else None,
+                                        torch.cuda.current_stream().cuda_stream)
         _capi.check(rc, "psf_generators_fwd")
         ctx.save_for_backward(x, w1, b1, w2, b2, *(gs if has_g else ()))
+        ctx.pre = pre
         ctx.desc = d
         ctx.has_g = has_g
         return out, v0
@@ -141,10 +149,12 @@ class _FusedGenerators(torch.autograd.Function):
             ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=x.device)
             with _Timed("bwd", 2):       # backward kernel + the fixed-order reduction of the per-CTA slices
                 rc = lib.psf_generators_bwd(C.byref(d), x.data_ptr(), _ptrs((w1, b1, w2, b2)), _ptrs(gs),
-                                            dout.data_ptr(), dv0.data_ptr() if ctx.has_g else None, dx.data_ptr(),
+                                            dout.data_ptr(), dv0.data_ptr() if ctx.has_g else None,
+                                            ctx.pre.data_ptr() if ctx.pre is not None else None, dx.data_ptr(),
                                             _ptrs(dfs), _ptrs(dgs), ws.data_ptr(), ws.numel(),
                                             torch.cuda.current_stream().cuda_stream)
         _capi.check(rc, "psf_generators_bwd")
+        ctx.pre = None
         return (dx, None, None, *dfs, *dgs)
 
 

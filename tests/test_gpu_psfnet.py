@@ -180,13 +180,15 @@ def test_fused_generators_full_size_equal_gemm_route():
         torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5 * float(b.abs().max()))
 
 
+@pytest.mark.parametrize("save_pre", [True, False])
 @pytest.mark.parametrize("B,n,n_W,L,C,Q", [(2, 256, 3, 9, 8, 1), (2, 256, 4, 9, 8, 4), (1, 1024, 2, 11, 16, 8),
                                            (3, 128, 2, 8, 3, 2)])
-def test_fused_generators_with_v_generator(B, n, n_W, L, C, Q):
+def test_fused_generators_with_v_generator(B, n, n_W, L, C, Q, save_pre, monkeypatch):
     """generate_all: every fs[m](data) and g(data) from one kernel; W comes out in the requested (quad-interleaved)
     row order, V0 in natural order; all gradients against the per-module fp64 evaluation."""
     from sparsefactorization_b200 import chain, generators
     from sparsefactorization_b200._psfnet import MLPBlock, generate_all
+    monkeypatch.setattr(generators, "SAVE_PREACTIVATIONS", save_pre)   # backward from saved / recomputed pre-activations
     torch.manual_seed(B * n + L + Q)
     fs = torch.nn.ModuleList([MLPBlock([32, "GELU"], 32, L) for _ in range(n_W)]).cuda()
     g = MLPBlock([32, "GELU"], 32, C).cuda()

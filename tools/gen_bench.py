@@ -33,7 +33,10 @@ def main():
     ap.add_argument("--B", type=int, default=132)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--gemm", type=int, default=0, help="also time the batched-GEMM route")
+    ap.add_argument("--recompute", type=int, default=1, help="1: backward recomputes the pre-activations")
     a = ap.parse_args()
+    from sparsefactorization_b200 import generators
+    generators.SAVE_PREACTIVATIONS = not a.recompute
     n_W = (a.n - 1).bit_length()
     L = n_W + 1
     torch.manual_seed(0)
