@@ -30,7 +30,6 @@ constexpr int GLP = 16;   // taps padded
 constexpr int kBlkFwd = GH * GE + GH + GH * GLP + GLP;  // w1[h][e], b1[h], w2t[h][l], b2[l]  = 1584 floats
 constexpr int kBlkBwd = GH * GE + GH + GLP * GH;        // w1[h][e], b1[h], w2[l][h]          = 1568 floats
 constexpr int kAccBlk = GH * GE + GH + GLP * GH + GLP;  // dW1, db1, dW2 (l-major, padded), db2 = 1584 floats
-constexpr int kTB = 128;                                 // backward: rows per tile == threads per CTA (3 CTAs per SM)
 constexpr int XS = GE + 4;                               // padded row stride of the staged tiles (bank-conflict free)
 constexpr int DS = GLP + 4;
 
@@ -278,8 +277,11 @@ __device__ __forceinline__ void rs_step(float* v, int M, bool hi) {
   }
 }
 
-template <bool kSaved>
-__global__ void __launch_bounds__(kTB, 3) psf_gen_bwd_kernel(const GenParams p) {
+template <int kTB, bool kSaved>
+__global__ void __launch_bounds__(kTB, 384 / kTB) psf_gen_bwd_kernel(const GenParams p) {
+  static_assert(kTB == 64 || kTB == 128, "tile sizes with a phase-2 mapping");
+  constexpr int KG1 = kTB / 16;  // row groups of phase 2a (16 output tiles x KG1 = kTB threads)
+  constexpr int KG2 = kTB / 8;   // row groups of phase 2b (8 output tiles x KG2 = kTB threads)
   extern __shared__ __align__(16) float gsm[];
   float* xs = gsm;                    // [kTB][XS]   x rows of the tile
   float* dps = xs + kTB * XS;       // [kTB][XS]   dpre
@@ -436,8 +438,8 @@ __global__ void __launch_bounds__(kTB, 3) psf_gen_bwd_kernel(const GenParams p) 
       float* acc_m = wsc + (long long)m * kAccBlk;
       // ---- phase 2a: dW1[h][e] += sum_rows dpre[row][h] * x[row][e]  (+ db1) -----------------
       {
-        const int kg = lane & 7;                                    // row group: rows rr*8 + kg
-        const int t16 = (lane >> 3) | (warp << 2);                  // 16 output tiles of 8 x 8
+        const int kg = lane & (KG1 - 1);                            // row group: rows rr*KG1 + kg
+        const int t16 = lane / KG1 + warp * (32 / KG1);             // 16 output tiles of 8 x 8
         const int hb = t16 >> 2, eb = t16 & 3;
         float2 v[32];  // v[i * 4 + j] = outputs (i, 2j), (i, 2j + 1) of the 8 x 8 tile
         float db[8];
@@ -446,8 +448,8 @@ __global__ void __launch_bounds__(kTB, 3) psf_gen_bwd_kernel(const GenParams p) 
 #pragma unroll
         for (int i = 0; i < 8; ++i) db[i] = 0.f;
 #pragma unroll 1
-        for (int rr = 0; rr < kTB / 8; ++rr) {
-          const int r = rr * 8 + kg;
+        for (int rr = 0; rr < kTB / KG1; ++rr) {
+          const int r = rr * KG1 + kg;
           const float4 d0 = lds4g(dps + r * XS + hb * 8), d1 = lds4g(dps + r * XS + hb * 8 + 4);
           const float4 a0 = lds4g(xs + r * XS + eb * 8), a1 = lds4g(xs + r * XS + eb * 8 + 4);
           const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
@@ -461,23 +463,40 @@ __global__ void __launch_bounds__(kTB, 3) psf_gen_bwd_kernel(const GenParams p) 
             db[i] += dd[i];
           }
         }
-        rs_step2<16>(v, 4, lane & 4);
-        rs_step2<8>(v, 2, lane & 2);
-        rs_step2<4>(v, 1, lane & 1);
-        const int i = ((lane & 4) ? 4 : 0) + ((lane & 2) ? 2 : 0) + (lane & 1);   // tile row this lane ends up owning
-        float* dst = acc_m + (hb * 8 + i) * GE + eb * 8;
-        red_add4(dst, v[0].x, v[0].y, v[1].x, v[1].y);
-        red_add4(dst + 4, v[2].x, v[2].y, v[3].x, v[3].y);
-        // bias gradient: every lane group holds the column sums of dpre; the eb == 0 tiles write them
-        rs_step<4>(db, 4, lane & 4);
-        rs_step<2>(db, 2, lane & 2);
-        rs_step<1>(db, 1, lane & 1);
-        if (eb == 0) red_add1(acc_m + GH * GE + hb * 8 + i, db[0]);
+        if constexpr (KG1 == 8) {
+          rs_step2<16>(v, 4, lane & 4);
+          rs_step2<8>(v, 2, lane & 2);
+          rs_step2<4>(v, 1, lane & 1);
+          const int i = ((lane & 4) ? 4 : 0) + ((lane & 2) ? 2 : 0) + (lane & 1);   // tile row this lane ends up owning
+          float* dst = acc_m + (hb * 8 + i) * GE + eb * 8;
+          red_add4(dst, v[0].x, v[0].y, v[1].x, v[1].y);
+          red_add4(dst + 4, v[2].x, v[2].y, v[3].x, v[3].y);
+          // bias gradient: every lane group holds the column sums of dpre; the eb == 0 tiles write them
+          rs_step<4>(db, 4, lane & 4);
+          rs_step<2>(db, 2, lane & 2);
+          rs_step<1>(db, 1, lane & 1);
+          if (eb == 0) red_add1(acc_m + GH * GE + hb * 8 + i, db[0]);
+        } else {  // four row groups: two reduce-scatter stages leave two tile rows per lane
+          rs_step2<16>(v, 2, lane & 2);
+          rs_step2<8>(v, 1, lane & 1);
+          const int i = ((lane & 2) ? 4 : 0) + ((lane & 1) ? 2 : 0);
+          float* dst = acc_m + (hb * 8 + i) * GE + eb * 8;
+          red_add4(dst, v[0].x, v[0].y, v[1].x, v[1].y);
+          red_add4(dst + 4, v[2].x, v[2].y, v[3].x, v[3].y);
+          red_add4(dst + GE, v[4].x, v[4].y, v[5].x, v[5].y);
+          red_add4(dst + GE + 4, v[6].x, v[6].y, v[7].x, v[7].y);
+          rs_step<4>(db, 2, lane & 2);
+          rs_step<2>(db, 1, lane & 1);
+          if (eb == 0) {
+            red_add1(acc_m + GH * GE + hb * 8 + i, db[0]);
+            red_add1(acc_m + GH * GE + hb * 8 + i + 1, db[1]);
+          }
+        }
       }
       // ---- phase 2b: dW2[l][h] += sum_rows dout[row][l] * hid[row][h]  (+ db2) ----------------
       {
-        const int kg = lane & 15;                                   // row group: rows rr*16 + kg
-        const int t8 = (lane >> 4) | (warp << 1);                   // 8 output tiles of 8 x 8
+        const int kg = lane & (KG2 - 1);                            // row group: rows rr*KG2 + kg
+        const int t8 = lane / KG2 + warp * (32 / KG2);              // 8 output tiles of 8 x 8
         const int lb = t8 >> 2, hb = t8 & 3;
         float2 v[32];  // v[i * 4 + j] = outputs (i, 2j), (i, 2j + 1) of the 8 x 8 tile
         float db[8];
@@ -486,8 +505,8 @@ __global__ void __launch_bounds__(kTB, 3) psf_gen_bwd_kernel(const GenParams p) 
 #pragma unroll
         for (int i = 0; i < 8; ++i) db[i] = 0.f;
 #pragma unroll 1
-        for (int rr = 0; rr < kTB / 16; ++rr) {
-          const int r = rr * 16 + kg;
+        for (int rr = 0; rr < kTB / KG2; ++rr) {
+          const int r = rr * KG2 + kg;
           const float4 d0 = lds4g(dos + r * DS + lb * 8), d1 = lds4g(dos + r * DS + lb * 8 + 4);
           const float4 a0 = lds4g(hs + r * XS + hb * 8), a1 = lds4g(hs + r * XS + hb * 8 + 4);
           const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
@@ -501,19 +520,33 @@ __global__ void __launch_bounds__(kTB, 3) psf_gen_bwd_kernel(const GenParams p) 
             db[i] += dd[i];
           }
         }
-        rs_step2<16>(v, 8, lane & 8);
-        rs_step2<8>(v, 4, lane & 4);
-        rs_step2<4>(v, 2, lane & 2);
-        rs_step2<2>(v, 1, lane & 1);
-        const int o = ((lane & 8) ? 32 : 0) + ((lane & 4) ? 16 : 0) + ((lane & 2) ? 8 : 0) + ((lane & 1) ? 4 : 0);
-        red_add4(acc_m + GH * GE + GH + (lb * 8 + (o >> 3)) * GH + hb * 8 + (o & 7), v[0].x, v[0].y, v[1].x, v[1].y);
-        rs_step<4>(db, 8, lane & 8);
-        rs_step<2>(db, 4, lane & 4);
-        rs_step<1>(db, 2, lane & 2);
-        db[0] += __shfl_xor_sync(0xffffffffu, db[0], 1);
-        if (hb == 0 && !(lane & 1)) {
-          const int l = lb * 8 + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
-          red_add1(acc_m + GH * GE + GH + GLP * GH + l, db[0]);
+        if constexpr (KG2 == 16) {
+          rs_step2<16>(v, 8, lane & 8);
+          rs_step2<8>(v, 4, lane & 4);
+          rs_step2<4>(v, 2, lane & 2);
+          rs_step2<2>(v, 1, lane & 1);
+          const int o = ((lane & 8) ? 32 : 0) + ((lane & 4) ? 16 : 0) + ((lane & 2) ? 8 : 0) + ((lane & 1) ? 4 : 0);
+          red_add4(acc_m + GH * GE + GH + (lb * 8 + (o >> 3)) * GH + hb * 8 + (o & 7), v[0].x, v[0].y, v[1].x, v[1].y);
+          rs_step<4>(db, 8, lane & 8);
+          rs_step<2>(db, 4, lane & 4);
+          rs_step<1>(db, 2, lane & 2);
+          db[0] += __shfl_xor_sync(0xffffffffu, db[0], 1);
+          if (hb == 0 && !(lane & 1)) {
+            const int l = lb * 8 + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
+            red_add1(acc_m + GH * GE + GH + GLP * GH + l, db[0]);
+          }
+        } else {  // eight row groups: three stages leave one tile row per lane
+          rs_step2<16>(v, 4, lane & 4);
+          rs_step2<8>(v, 2, lane & 2);
+          rs_step2<4>(v, 1, lane & 1);
+          const int i = ((lane & 4) ? 4 : 0) + ((lane & 2) ? 2 : 0) + (lane & 1);
+          float* dst = acc_m + GH * GE + GH + (lb * 8 + i) * GH + hb * 8;
+          red_add4(dst, v[0].x, v[0].y, v[1].x, v[1].y);
+          red_add4(dst + 4, v[2].x, v[2].y, v[3].x, v[3].y);
+          rs_step<4>(db, 4, lane & 4);
+          rs_step<2>(db, 2, lane & 2);
+          rs_step<1>(db, 1, lane & 1);
+          if (hb == 0) red_add1(acc_m + GH * GE + GH + GLP * GH + lb * 8 + i, db[0]);
         }
       }
     }
@@ -565,6 +598,10 @@ int gen_grid(int per_sm) {
   return sms * per_sm;
 }
 
+#ifndef PSF_GEN_TB
+#define PSF_GEN_TB 128
+#endif
+constexpr int kTB = PSF_GEN_TB;   // backward: rows per tile == threads per CTA; 384 / kTB CTAs per SM (tools/gen_bench.py)
 constexpr int kSmemBwd = (3 * kTB * XS + kTB * DS + kBlkBwd) * 4;
 
 int gen_check(int64_t rows, int n_W, int E, int H, int L) {
@@ -572,8 +609,8 @@ int gen_check(int64_t rows, int n_W, int E, int H, int L) {
   if (n_W * kBlkFwd * 4 > 110 * 1024) return PSF_ERR_UNSUPPORTED;  // forward keeps every generator's weights resident
   if (!g_gen_attr) {
     if (cudaFuncSetAttribute(psf_gen_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(psf_gen_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBwd) != cudaSuccess ||
-        cudaFuncSetAttribute(psf_gen_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBwd) != cudaSuccess) {
+        cudaFuncSetAttribute(psf_gen_bwd_kernel<kTB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBwd) != cudaSuccess ||
+        cudaFuncSetAttribute(psf_gen_bwd_kernel<kTB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBwd) != cudaSuccess) {
       cudaGetLastError();
       return PSF_ERR_UNSUPPORTED;
     }
@@ -588,7 +625,7 @@ extern "C" {
 
 size_t psf_generators_workspace_bytes(int n_W) {
   if (n_W < 1) return 0;
-  return psf_round256((size_t)gen_grid(3) * (size_t)(n_W + 1) * kAccBlk * sizeof(float));
+  return psf_round256((size_t)gen_grid(384 / kTB) * (size_t)(n_W + 1) * kAccBlk * sizeof(float));
 }
 
 static int gen_fill(GenParams& p, const psf_gen_desc* d, const float* x, const psf_mlp_params& fs, const psf_mlp_params& g) {
@@ -660,7 +697,7 @@ int psf_generators_bwd(const psf_gen_desc* d, const float* x, psf_mlp_params fs,
   if (workspace == nullptr || workspace_bytes < psf_generators_workspace_bytes(d->n_W)) return PSF_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   const long long ntiles = (d->rows + kTB - 1) / kTB;
-  long long grid = gen_grid(3);
+  long long grid = gen_grid(384 / kTB);
   if (grid > ntiles) grid = ntiles;
   if (grid < 1) grid = 1;
   PSF_CUDA_TRY(cudaMemsetAsync(workspace, 0, (size_t)grid * p.n_gen * kAccBlk * sizeof(float), st));
@@ -671,9 +708,9 @@ int psf_generators_bwd(const psf_gen_desc* d, const float* x, psf_mlp_params fs,
   p.pre = const_cast<float*>(pre_saved);
   if (d->rows > 0) {
     if (pre_saved != nullptr)
-      psf_gen_bwd_kernel<true><<<(unsigned)grid, kTB, kSmemBwd, st>>>(p);
+      psf_gen_bwd_kernel<kTB, true><<<(unsigned)grid, kTB, kSmemBwd, st>>>(p);
     else
-      psf_gen_bwd_kernel<false><<<(unsigned)grid, kTB, kSmemBwd, st>>>(p);
+      psf_gen_bwd_kernel<kTB, false><<<(unsigned)grid, kTB, kSmemBwd, st>>>(p);
     PSF_CUDA_TRY(cudaGetLastError());
   }
   GenGrads gg = {dfs.W1, dfs.b1, dfs.W2, dfs.b2, dg.W1, dg.b1, dg.W2, dg.b2};
