@@ -510,6 +510,7 @@ __global__ void __launch_bounds__(kNWB * 32, PSF2_MINB_BWD) psf_chain2_bwd_kerne
       float* dWmb = p.dW + (long long)(m - 1) * p.sWf + (long long)b * p.sWb;
       const bool last = (m == 1);
       const bool first = (m == p.n_W);
+      const bool even_step = !(step & 1);
 
       mbar_wait(vbar, vparity);  // G_m block has landed in shared memory
       vparity ^= 1u;
@@ -615,7 +616,9 @@ __global__ void __launch_bounds__(kNWB * 32, PSF2_MINB_BWD) psf_chain2_bwd_kerne
               tmem_ld32(twarp + (uint32_t)pp * 32u, R);  // lands behind the last group of local taps
             }
 #else
-            if (p.residual && !first && !(kAbl & 4)) {
+            // the buffer is touched every OTHER factor: an even step adds both G_m (the state) and G_{m-1} (the
+            // accumulators it has just finished), so the odd step in between has nothing left to add
+            if (p.residual && ((even_step && !first) || (!even_step && last)) && !(kAbl & 4)) {
 #pragma unroll
               for (int ch = 0; ch < CT; ++ch) R[ch] = ldcg4_keep(racc + ch * J + j, keep);
             }
@@ -646,17 +649,21 @@ __global__ void __launch_bounds__(kNWB * 32, PSF2_MINB_BWD) psf_chain2_bwd_kerne
               }
             }
 #else
-            if (p.residual) {
+            if (p.residual && even_step) {
 #pragma unroll
               for (int ch = 0; ch < CT; ++ch) {
-                float4 own = lds4(state + ch * J + j);
-                if (!first) add4(own, R[ch]);
-                if (!last && !(kAbl & 4)) {
-                  stcg4_keep(racc + ch * J + j, own, keep);
+                float4 own = lds4(state + ch * J + j);      // G_m
+                if (!first) add4(own, R[ch]);               // + the pairs before
+                if (!last) {
+                  add4(own, acc[ch]);                       // + G_{m-1}
+                  if (!(kAbl & 4)) stcg4_keep(racc + ch * J + j, own, keep);
                 } else {
-                  add4(acc[ch], own);
+                  add4(acc[ch], own);                       // dV0 = G_0 + G_1 + pairs
                 }
               }
+            } else if (p.residual && last) {                // odd last step: G_1 was added one step ago
+#pragma unroll
+              for (int ch = 0; ch < CT; ++ch) add4(acc[ch], R[ch]);
             }
 #endif
           } else if constexpr (g == 1) {
