@@ -72,8 +72,13 @@ namespace {
 #define PSF2_ABLATE 0
 #endif
 constexpr int kAbl = PSF2_ABLATE;
-constexpr int kNWF = PSF2_NW_FWD;
-constexpr int kNWB = PSF2_NW_BWD;
+// per block size J = 2^LOGJ rows (J / 128 warp tiles): warps per CTA and CTAs per SM.  J = 2048 uses the tuned
+// shapes above; smaller blocks (n < 2048: one CTA per sample) run one pass with one warp per tile and as many
+// CTAs per SM as keep 16 (forward) / 12 (backward) warps resident.
+__host__ __device__ constexpr int nw_fwd(int logj) { return logj >= 11 ? PSF2_NW_FWD : ((1 << logj) / 128 < 8 ? (1 << logj) / 128 : 8); }
+__host__ __device__ constexpr int minb_fwd(int logj) { return logj >= 11 ? PSF2_MINB_FWD : 16 / nw_fwd(logj); }
+__host__ __device__ constexpr int nw_bwd(int logj) { return logj >= 11 ? PSF2_NW_BWD : ((1 << logj) / 128 < 4 ? (1 << logj) / 128 : 4); }
+__host__ __device__ constexpr int minb_bwd(int logj) { return logj >= 11 ? PSF2_MINB_BWD : 12 / nw_bwd(logj); }
 constexpr int kTileRows = 128;       // rows per warp tile (32 lanes x one quad)
 
 struct Chain2Params {
@@ -115,7 +120,7 @@ __device__ __forceinline__ void static_for(F&& f) {
 //   W values of taps 1,2 separately (they straddle two quads), so its sequence skips them.
 template <int LOGJ, int LOGQ, bool BWD>
 struct Geo {
-  static constexpr int NW = BWD ? kNWB : kNWF;
+  static constexpr int NW = BWD ? nw_bwd(LOGJ) : nw_fwd(LOGJ);
   static constexpr int NT = (1 << LOGJ) / kTileRows;  // warp tiles per CTA block
   static constexpr int J = 1 << LOGJ;
   static constexpr int Q = 1 << LOGQ;
@@ -251,7 +256,7 @@ __device__ __forceinline__ void refresh_block(uint32_t state_u32, uint32_t vbar,
 // Forward
 // ---------------------------------------------------------------------------------------------
 template <int LOGJ, int LOGQ>
-__global__ void __launch_bounds__(kNWF * 32, PSF2_MINB_FWD) psf_chain2_fwd_kernel(const Chain2Params p) {
+__global__ void __launch_bounds__(nw_fwd(LOGJ) * 32, minb_fwd(LOGJ)) psf_chain2_fwd_kernel(const Chain2Params p) {
   using G = Geo<LOGJ, LOGQ, false>;
   constexpr int J = G::J, Q = G::Q, NQ = G::NQ, kNW = G::NW;
   constexpr int PFW = PSF2_PFW_FWD;  // W registers in flight (taps)
@@ -434,7 +439,7 @@ __global__ void __launch_bounds__(kNWF * 32, PSF2_MINB_FWD) psf_chain2_fwd_kerne
 // one shifted read of G feeds both; V_{m-1}[j,:] (saved by the forward pass) sits in registers.
 // ---------------------------------------------------------------------------------------------
 template <int LOGJ, int LOGQ>
-__global__ void __launch_bounds__(kNWB * 32, PSF2_MINB_BWD) psf_chain2_bwd_kernel(const Chain2Params p) {
+__global__ void __launch_bounds__(nw_bwd(LOGJ) * 32, minb_bwd(LOGJ)) psf_chain2_bwd_kernel(const Chain2Params p) {
   using G = Geo<LOGJ, LOGQ, true>;
   constexpr int J = G::J, Q = G::Q, NQ = G::NQ, kNW = G::NW;
   constexpr int PFW = PSF2_PFW_BWD;
@@ -463,7 +468,7 @@ __global__ void __launch_bounds__(kNWB * 32, PSF2_MINB_BWD) psf_chain2_bwd_kerne
   // tensor memory for the residual accumulator: 32 columns per (warp group of 4, pass); power of two >= 32
   constexpr uint32_t kRaccColsRaw = ((kNW + 3) / 4) * G::NPASS * 32;
   constexpr uint32_t kRaccCols = kRaccColsRaw <= 32 ? 32 : kRaccColsRaw <= 64 ? 64 : kRaccColsRaw <= 128 ? 128 : kRaccColsRaw <= 256 ? 256 : 512;
-  static_assert(kRaccCols * PSF2_MINB_BWD <= 512, "tensor memory over-subscribed");
+  static_assert(kRaccCols * minb_bwd(LOGJ) <= 512, "tensor memory over-subscribed");
   const uint32_t tslot = vbar + 16;  // shared-memory word that receives the TMEM base address
   if (warp == 0) tmem_alloc(tslot, kRaccCols);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -748,7 +753,8 @@ __global__ void __launch_bounds__(kNWB * 32, PSF2_MINB_BWD) psf_chain2_bwd_kerne
 // ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
-constexpr int kLogJ = 11;
+constexpr int kLogJ = 11;      // block size of the clustered shapes (n >= 2048)
+constexpr int kLogJMin = 7;    // smallest single-CTA shape (n = 128)
 
 int env_int2(const char* name, int dflt) {
   const char* v = std::getenv(name);
@@ -756,40 +762,39 @@ int env_int2(const char* name, int dflt) {
   return std::atoi(v);
 }
 
-const void* fwd2_kernel_for(int logq) {
-  switch (logq) {
-    case 0: return (const void*)psf_chain2_fwd_kernel<kLogJ, 0>;
-    case 1: return (const void*)psf_chain2_fwd_kernel<kLogJ, 1>;
-    case 2: return (const void*)psf_chain2_fwd_kernel<kLogJ, 2>;
-    default: return (const void*)psf_chain2_fwd_kernel<kLogJ, 3>;
+// kernel table: (logj, logq) with logq > 0 only for logj == kLogJ
+#define PSF2_KERNEL_CASES(K)                                            \
+  if (logj == 7) return (const void*)K<7, 0>;                           \
+  if (logj == 8) return (const void*)K<8, 0>;                           \
+  if (logj == 9) return (const void*)K<9, 0>;                           \
+  if (logj == 10) return (const void*)K<10, 0>;                         \
+  switch (logq) {                                                       \
+    case 0: return (const void*)K<kLogJ, 0>;                            \
+    case 1: return (const void*)K<kLogJ, 1>;                            \
+    case 2: return (const void*)K<kLogJ, 2>;                            \
+    default: return (const void*)K<kLogJ, 3>;                           \
   }
-}
-const void* bwd2_kernel_for(int logq) {
-  switch (logq) {
-    case 0: return (const void*)psf_chain2_bwd_kernel<kLogJ, 0>;
-    case 1: return (const void*)psf_chain2_bwd_kernel<kLogJ, 1>;
-    case 2: return (const void*)psf_chain2_bwd_kernel<kLogJ, 2>;
-    default: return (const void*)psf_chain2_bwd_kernel<kLogJ, 3>;
-  }
-}
+const void* fwd2_kernel_for(int logj, int logq) { PSF2_KERNEL_CASES(psf_chain2_fwd_kernel) }
+const void* bwd2_kernel_for(int logj, int logq) { PSF2_KERNEL_CASES(psf_chain2_bwd_kernel) }
 
-constexpr int kSmem2 = CT * (1 << kLogJ) * 4 + 64;
+int smem2(int logj) { return CT * (1 << logj) * 4 + 64; }
+int threads2(bool bwd, int logj) { return (bwd ? nw_bwd(logj) : nw_fwd(logj)) * 32; }
 
 bool g_attr2_done = false;
-int g_res2[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+int g_res2[2][8] = {{0}, {0}};   // [bwd][slot]: slots 0..3 = logj 7..10, 4..7 = logj 11 with logq 0..3
 
-int resident2(bool bwd, int logq) {
-  int& slot = g_res2[bwd ? 1 : 0][logq];
+int resident2(bool bwd, int logj, int logq) {
+  int& slot = g_res2[bwd ? 1 : 0][logj < kLogJ ? logj - kLogJMin : 4 + logq];
   if (slot > 0) return slot;
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const void* kernel = bwd ? bwd2_kernel_for(logq) : fwd2_kernel_for(logq);
+  const void* kernel = bwd ? bwd2_kernel_for(logj, logq) : fwd2_kernel_for(logj, logq);
   const int Q = 1 << logq;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(Q * sms * 2), 1, 1);
-  cfg.blockDim = dim3((unsigned)((bwd ? kNWB : kNWF) * 32), 1, 1);
-  cfg.dynamicSmemBytes = (size_t)kSmem2;
+  cfg.gridDim = dim3((unsigned)(Q * sms * 32), 1, 1);
+  cfg.blockDim = dim3((unsigned)threads2(bwd, logj), 1, 1);
+  cfg.dynamicSmemBytes = (size_t)smem2(logj);
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)Q;
@@ -806,13 +811,13 @@ int resident2(bool bwd, int logq) {
   return ncl;
 }
 
-int launch2(const void* kernel, const Chain2Params& cp, int logq, int resident, int threads, cudaStream_t st) {
+int launch2(const void* kernel, const Chain2Params& cp, int logj, int logq, int resident, int threads, cudaStream_t st) {
   const int Q = 1 << logq;
   cudaLaunchConfig_t cfg = {};
   const int clusters = resident < cp.B ? resident : cp.B;
   cfg.gridDim = dim3((unsigned)(clusters * Q), 1, 1);
   cfg.blockDim = dim3((unsigned)threads, 1, 1);
-  cfg.dynamicSmemBytes = (size_t)kSmem2;
+  cfg.dynamicSmemBytes = (size_t)smem2(logj);
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -844,11 +849,19 @@ int psf_chain2_interleave_for(const PsfChainArgs& a) {
   if (a.C != CT || a.n_W < 1 || a.B < 1 || a.B > (1 << 20)) return 0;
   int logn = 0;
   while ((int64_t(1) << logn) < a.n) ++logn;
-  if ((int64_t(1) << logn) != a.n || logn < kLogJ || logn > kLogJ + 3) return 0;
+  if ((int64_t(1) << logn) != a.n || logn < kLogJMin || logn > kLogJ + 3) return 0;
   if (a.L != logn + 1) return 0;
   for (int k = 0; k < a.L; ++k)
     if (a.offs.o[k] != (k == 0 ? 0 : (1 << (k - 1)))) return 0;
-  return 1 << (logn - kLogJ);
+  return logn <= kLogJ ? 1 : 1 << (logn - kLogJ);
+}
+
+static void geom2(const PsfChainArgs& a, int Q, int* logj, int* logq) {
+  int logn = 0;
+  while ((int64_t(1) << logn) < a.n) ++logn;
+  *logq = 0;
+  while ((1 << *logq) < Q) ++*logq;
+  *logj = logn - *logq;
 }
 
 int psf_chain2_plan(const PsfChainArgs& a, PsfFusedPlan* plan) {
@@ -857,24 +870,27 @@ int psf_chain2_plan(const PsfChainArgs& a, PsfFusedPlan* plan) {
   const int il = a.interleave < 1 ? 1 : a.interleave;
   if (il != Q) return PSF_ERR_UNSUPPORTED;
   if (a.ws.row != 1 || (a.ws.factor & 3) || (a.ws.sample & 3) || (a.ws.tap & 3)) return PSF_ERR_UNSUPPORTED;
-  int logq = 0;
-  while ((1 << logq) < Q) ++logq;
+  int logj, logq;
+  geom2(a, Q, &logj, &logq);
   if (!g_attr2_done) {
-    for (int lq = 0; lq < 4; ++lq)
-      if (cudaFuncSetAttribute(fwd2_kernel_for(lq), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2) != cudaSuccess ||
-          cudaFuncSetAttribute(bwd2_kernel_for(lq), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2) != cudaSuccess) {
-        cudaGetLastError();
-        return PSF_ERR_UNSUPPORTED;
-      }
+    for (int lj = kLogJMin; lj <= kLogJ; ++lj)
+      for (int lq = 0; lq < (lj == kLogJ ? 4 : 1); ++lq)
+        if (cudaFuncSetAttribute(fwd2_kernel_for(lj, lq), cudaFuncAttributeMaxDynamicSharedMemorySize, smem2(lj)) !=
+                cudaSuccess ||
+            cudaFuncSetAttribute(bwd2_kernel_for(lj, lq), cudaFuncAttributeMaxDynamicSharedMemorySize, smem2(lj)) !=
+                cudaSuccess) {
+          cudaGetLastError();
+          return PSF_ERR_UNSUPPORTED;
+        }
     g_attr2_done = true;
   }
-  const int rf = resident2(false, logq), rb = resident2(true, logq);
+  const int rf = resident2(false, logj, logq), rb = resident2(true, logj, logq);
   if (rf < 1 || rb < 1) return PSF_ERR_UNSUPPORTED;
   plan->cluster = Q;
-  plan->rows_per_cta = 1 << kLogJ;
-  plan->threads = kNWF * 32;
-  plan->smem_bytes = kSmem2;
-  plan->smem_bytes_bwd = kSmem2;
+  plan->rows_per_cta = 1 << logj;
+  plan->threads = threads2(false, logj);
+  plan->smem_bytes = smem2(logj);
+  plan->smem_bytes_bwd = smem2(logj);
   plan->resident = rf;
   plan->resident_bwd = rb;
   plan->stages = 0;
@@ -888,8 +904,8 @@ int psf_chain2_fwd(const PsfChainArgs& a, const float* W, const float* V0, float
   PsfFusedPlan plan;
   int rc = psf_chain2_plan(a, &plan);
   if (rc) return rc;
-  int logq = 0;
-  while ((1 << logq) < plan.cluster) ++logq;
+  int logj, logq;
+  geom2(a, plan.cluster, &logj, &logq);
   Chain2Params cp = {};
   cp.W = W;
   cp.Vin = V0;
@@ -897,7 +913,7 @@ int psf_chain2_fwd(const PsfChainArgs& a, const float* W, const float* V0, float
   cp.states = ws;
   cp.save_states = save_states;
   fill2(cp, a);
-  return launch2(fwd2_kernel_for(logq), cp, logq, plan.resident, kNWF * 32, st);
+  return launch2(fwd2_kernel_for(logj, logq), cp, logj, logq, plan.resident, threads2(false, logj), st);
 }
 
 int psf_chain2_bwd(const PsfChainArgs& a, const float* W, const float* dOut, float* dW, float* dV0, float* ws,
@@ -905,8 +921,8 @@ int psf_chain2_bwd(const PsfChainArgs& a, const float* W, const float* dOut, flo
   PsfFusedPlan plan;
   int rc = psf_chain2_plan(a, &plan);
   if (rc) return rc;
-  int logq = 0;
-  while ((1 << logq) < plan.cluster) ++logq;
+  int logj, logq;
+  geom2(a, plan.cluster, &logj, &logq);
   const long long S = a.B * a.n * a.C;
   Chain2Params cp = {};
   cp.W = W;
@@ -918,5 +934,5 @@ int psf_chain2_bwd(const PsfChainArgs& a, const float* W, const float* dOut, flo
   cp.racc = cp.gx + 2 * S;
   cp.save_states = 1;
   fill2(cp, a);
-  return launch2(bwd2_kernel_for(logq), cp, logq, plan.resident_bwd, kNWB * 32, st);
+  return launch2(bwd2_kernel_for(logj, logq), cp, logj, logq, plan.resident_bwd, threads2(true, logj), st);
 }

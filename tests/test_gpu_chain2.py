@@ -41,6 +41,10 @@ def test_relayout_interleave_matches_row_permutation():
 
 
 @pytest.mark.parametrize("B,n,residual", [
+    (5, 128, True),       # single-CTA shapes below 2048 rows: one warp per 128-row tile, one pass (cfg1 shape)
+    (3, 256, False),
+    (40, 512, True),
+    (3, 1024, True),
     (3, 2048, True),      # Q = 1: no cluster, tap 3 is the first local tap
     (2, 2048, False),
     (3, 4096, True),      # Q = 2
