@@ -138,7 +138,8 @@ int psf_w_relayout_ex(psf_dtype dtype, const void* src, psf_wstrides ss, int src
                       psf_stream_t stream);
 
 /* Row interleave Q the fastest fused kernel wants for this problem (desc.interleave and desc.ws are
- * ignored): Q > 1 for f32, C = 8, n = 2^p in [4096, 16384], L = p+1 chord offsets; otherwise 1. */
+ * ignored): Q = n/2048 for f32, C = 8, n = 2^p in [4096, 16384], L = p+1 chord offsets; n/4096 for
+ * n = 32768, 65536; otherwise 1. */
 int psf_chain_preferred_interleave(const psf_chain_desc* d);
 
 /* Which fused kernel generation psf_chain_fwd would launch for this descriptor: 2 (quad-interleaved

@@ -75,10 +75,11 @@ constexpr int kAbl = PSF2_ABLATE;
 // per block size J = 2^LOGJ rows (J / 128 warp tiles): warps per CTA and CTAs per SM.  J = 2048 uses the tuned
 // shapes above; smaller blocks (n < 2048: one CTA per sample) run one pass with one warp per tile and as many
 // CTAs per SM as keep 16 (forward) / 12 (backward) warps resident.
-__host__ __device__ constexpr int nw_fwd(int logj) { return logj >= 11 ? PSF2_NW_FWD : ((1 << logj) / 128 < 8 ? (1 << logj) / 128 : 8); }
-__host__ __device__ constexpr int minb_fwd(int logj) { return logj >= 11 ? PSF2_MINB_FWD : 16 / nw_fwd(logj); }
-__host__ __device__ constexpr int nw_bwd(int logj) { return logj >= 11 ? PSF2_NW_BWD : ((1 << logj) / 128 < 4 ? (1 << logj) / 128 : 4); }
-__host__ __device__ constexpr int minb_bwd(int logj) { return logj >= 11 ? PSF2_MINB_BWD : 12 / nw_bwd(logj); }
+// J = 4096 (n = 32768 / 65536: 128 KB of state, one CTA per SM) runs 16 / 8 warps.
+__host__ __device__ constexpr int nw_fwd(int logj) { return logj >= 12 ? 16 : logj == 11 ? PSF2_NW_FWD : ((1 << logj) / 128 < 8 ? (1 << logj) / 128 : 8); }
+__host__ __device__ constexpr int minb_fwd(int logj) { return logj >= 12 ? 1 : logj == 11 ? PSF2_MINB_FWD : 16 / nw_fwd(logj); }
+__host__ __device__ constexpr int nw_bwd(int logj) { return logj >= 12 ? 8 : logj == 11 ? PSF2_NW_BWD : ((1 << logj) / 128 < 4 ? (1 << logj) / 128 : 4); }
+__host__ __device__ constexpr int minb_bwd(int logj) { return logj >= 12 ? 1 : logj == 11 ? PSF2_MINB_BWD : 12 / nw_bwd(logj); }
 constexpr int kTileRows = 128;       // rows per warp tile (32 lanes x one quad)
 
 struct Chain2Params {
@@ -753,8 +754,9 @@ __global__ void __launch_bounds__(nw_bwd(LOGJ) * 32, minb_bwd(LOGJ)) psf_chain2_
 // ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
-constexpr int kLogJ = 11;      // block size of the clustered shapes (n >= 2048)
+constexpr int kLogJ = 11;      // block size of the clustered shapes n = 2048 .. 16384
 constexpr int kLogJMin = 7;    // smallest single-CTA shape (n = 128)
+constexpr int kLogJBig = 12;   // n = 32768 (8 CTAs) and n = 65536 (16 CTAs: non-portable cluster size)
 
 int env_int2(const char* name, int dflt) {
   const char* v = std::getenv(name);
@@ -768,6 +770,7 @@ int env_int2(const char* name, int dflt) {
   if (logj == 8) return (const void*)K<8, 0>;                           \
   if (logj == 9) return (const void*)K<9, 0>;                           \
   if (logj == 10) return (const void*)K<10, 0>;                         \
+  if (logj == 12) return logq == 3 ? (const void*)K<12, 3> : (const void*)K<12, 4>; \
   switch (logq) {                                                       \
     case 0: return (const void*)K<kLogJ, 0>;                            \
     case 1: return (const void*)K<kLogJ, 1>;                            \
@@ -781,10 +784,10 @@ int smem2(int logj) { return CT * (1 << logj) * 4 + 64; }
 int threads2(bool bwd, int logj) { return (bwd ? nw_bwd(logj) : nw_fwd(logj)) * 32; }
 
 bool g_attr2_done = false;
-int g_res2[2][8] = {{0}, {0}};   // [bwd][slot]: slots 0..3 = logj 7..10, 4..7 = logj 11 with logq 0..3
+int g_res2[2][10] = {{0}, {0}};  // [bwd][slot]: slots 0..3 = logj 7..10, 4..7 = logj 11 with logq 0..3, 8..9 = logj 12
 
 int resident2(bool bwd, int logj, int logq) {
-  int& slot = g_res2[bwd ? 1 : 0][logj < kLogJ ? logj - kLogJMin : 4 + logq];
+  int& slot = g_res2[bwd ? 1 : 0][logj < kLogJ ? logj - kLogJMin : (logj == kLogJ ? 4 + logq : 8 + (logq - 3))];
   if (slot > 0) return slot;
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
@@ -803,6 +806,10 @@ int resident2(bool bwd, int logj, int logq) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int ncl = 0;
+  if (Q > 8 && cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
   if (cudaOccupancyMaxActiveClusters(&ncl, kernel, &cfg) != cudaSuccess || ncl < 1) {
     cudaGetLastError();
     return 0;
@@ -849,11 +856,11 @@ int psf_chain2_interleave_for(const PsfChainArgs& a) {
   if (a.C != CT || a.n_W < 1 || a.B < 1 || a.B > (1 << 20)) return 0;
   int logn = 0;
   while ((int64_t(1) << logn) < a.n) ++logn;
-  if ((int64_t(1) << logn) != a.n || logn < kLogJMin || logn > kLogJ + 3) return 0;
+  if ((int64_t(1) << logn) != a.n || logn < kLogJMin || logn > kLogJBig + 4) return 0;
   if (a.L != logn + 1) return 0;
   for (int k = 0; k < a.L; ++k)
     if (a.offs.o[k] != (k == 0 ? 0 : (1 << (k - 1)))) return 0;
-  return logn <= kLogJ ? 1 : 1 << (logn - kLogJ);
+  return logn <= kLogJ ? 1 : (logn <= kLogJ + 3 ? 1 << (logn - kLogJ) : 1 << (logn - kLogJBig));
 }
 
 static void geom2(const PsfChainArgs& a, int Q, int* logj, int* logq) {
@@ -873,8 +880,8 @@ int psf_chain2_plan(const PsfChainArgs& a, PsfFusedPlan* plan) {
   int logj, logq;
   geom2(a, Q, &logj, &logq);
   if (!g_attr2_done) {
-    for (int lj = kLogJMin; lj <= kLogJ; ++lj)
-      for (int lq = 0; lq < (lj == kLogJ ? 4 : 1); ++lq)
+    for (int lj = kLogJMin; lj <= kLogJBig; ++lj)
+      for (int lq = (lj == kLogJBig ? 3 : 0); lq < (lj == kLogJBig ? 5 : (lj == kLogJ ? 4 : 1)); ++lq)
         if (cudaFuncSetAttribute(fwd2_kernel_for(lj, lq), cudaFuncAttributeMaxDynamicSharedMemorySize, smem2(lj)) !=
                 cudaSuccess ||
             cudaFuncSetAttribute(bwd2_kernel_for(lj, lq), cudaFuncAttributeMaxDynamicSharedMemorySize, smem2(lj)) !=
