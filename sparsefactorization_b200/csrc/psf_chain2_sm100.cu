@@ -92,6 +92,7 @@ struct Chain2Params {
   float* racc;        // bwd residual accumulator, per cluster [ncl][Q][8][J]
   long long sWf, sWb, sWt;  // factor / sample / tap strides of W and dW (elements); row stride 1
   int B, n_W, residual, save_states;
+  int G;              // 8-channel slabs per sample (C = 8 G): slab s of sample b is pseudo-sample b*G + s
   int dbg;
 };
 
@@ -243,6 +244,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float4 (&v)[CT]) {
       : "memory");
 }
 
+__device__ __forceinline__ void red_add4g(float* p, const float4& v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void red_add1g(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 __device__ __forceinline__ void st_cs2(float* p, float a, float b) { __stcs(reinterpret_cast<float2*>(p), make_float2(a, b)); }
 
 // this CTA's block of a published state -> shared memory (8 channel planes of J floats, contiguous)
@@ -282,8 +287,12 @@ __global__ void __launch_bounds__(nw_fwd(LOGJ) * 32, minb_fwd(LOGJ)) psf_chain2_
   uint32_t vparity = 0;
   bool cw_pending = false;
 
-  for (int b = cid; b < p.B; b += ncl) {
-    float* st0 = p.states + (long long)b * plane;  // slot 0 = V_0 (residual operand, saved state 0)
+  const int NP = p.B * p.G;           // pseudo-samples (sample, 8-channel slab); states are indexed by them
+  const int rs = CT * p.G;            // floats per row of V0 / out
+  for (int bp = cid; bp < NP; bp += ncl) {
+    const int b = bp / p.G;           // W belongs to the sample
+    const int c0 = (bp - b * p.G) * CT;
+    float* st0 = p.states + (long long)bp * plane;  // slot 0 = V_0 (residual operand, saved state 0)
     // ---- prologue: V0 rows of this CTA (natural layout) -> state slot 0 ------------------------
 #pragma unroll 1
     for (int pp = 0; pp < G::NPASS; ++pp) {
@@ -292,7 +301,7 @@ __global__ void __launch_bounds__(nw_fwd(LOGJ) * 32, minb_fwd(LOGJ)) psf_chain2_
       const int j = 4 * lq;
       const int i0 = 4 * (lq * Q + q);
       float4 pl[CT];
-      load_rows_natural(p.Vin + ((long long)b * n + i0) * CT, pl);
+      load_rows_strided(p.Vin + ((long long)b * n + i0) * rs + c0, rs, pl);
 #pragma unroll
       for (int ch = 0; ch < CT; ++ch) st_cg4(st0 + q * blk + ch * J + j, pl[ch]);
     }
@@ -307,8 +316,8 @@ __global__ void __launch_bounds__(nw_fwd(LOGJ) * 32, minb_fwd(LOGJ)) psf_chain2_
     for (int m = 1; m <= p.n_W; ++m) {
       const int slot_prev = (p.save_states || m == 1) ? (m - 1) : 1 + ((m - 1) & 1);
       const int slot_next = p.save_states ? m : 1 + (m & 1);
-      const float* prev = p.states + ((long long)slot_prev * p.B + b) * plane;
-      float* next = p.states + ((long long)slot_next * p.B + b) * plane;
+      const float* prev = p.states + ((long long)slot_prev * NP + bp) * plane;
+      float* next = p.states + ((long long)slot_next * NP + bp) * plane;
       const bool last = (m == p.n_W);
       const float* Wmb = p.W + (long long)(m - 1) * p.sWf + (long long)b * p.sWb + q * J;
 
@@ -418,7 +427,7 @@ __global__ void __launch_bounds__(nw_fwd(LOGJ) * 32, minb_fwd(LOGJ)) psf_chain2_
           for (int ch = 0; ch < CT; ++ch)
             if (!(kAbl & 32) || acc[ch].x == 123.456f) st_cg4(next + q * blk + ch * J + j, acc[ch]);
         } else {
-          store_rows_natural(p.Vout + ((long long)b * n + 4 * (lq * Q + q)) * CT, acc);
+          store_rows_strided(p.Vout + ((long long)b * n + 4 * (lq * Q + q)) * rs + c0, rs, acc);
         }
       }
       if (!last) {
@@ -486,7 +495,12 @@ __global__ void __launch_bounds__(nw_bwd(LOGJ) * 32, minb_bwd(LOGJ)) psf_chain2_
   float* gx1 = p.gx + ((long long)ncl + cid) * plane;
   float* racc = p.racc + (long long)cid * plane + q * blk;
 
-  for (int b = cid; b < p.B; b += ncl) {
+  const int NP = p.B * p.G;           // pseudo-samples (sample, 8-channel slab)
+  const int rs = CT * p.G;            // floats per row of dOut / dV0
+  const bool multi = p.G > 1;         // several slabs add into the same dW: red.add on a pre-zeroed buffer
+  for (int bp = cid; bp < NP; bp += ncl) {
+    const int b = bp / p.G;
+    const int c0 = (bp - b * p.G) * CT;
     // ---- prologue: dOut rows of this CTA -> exchange slot 0 ------------------------------------
 #pragma unroll 1
     for (int pp = 0; pp < G::NPASS; ++pp) {
@@ -495,7 +509,7 @@ __global__ void __launch_bounds__(nw_bwd(LOGJ) * 32, minb_bwd(LOGJ)) psf_chain2_
       const int j = 4 * lq;
       const int i0 = 4 * (lq * Q + q);
       float4 pl[CT];
-      load_rows_natural(p.Vin + ((long long)b * n + i0) * CT, pl);
+      load_rows_strided(p.Vin + ((long long)b * n + i0) * rs + c0, rs, pl);
 #pragma unroll
       for (int ch = 0; ch < CT; ++ch) stcg4_keep(gx0 + q * blk + ch * J + j, pl[ch], keep);
     }
@@ -511,7 +525,7 @@ __global__ void __launch_bounds__(nw_bwd(LOGJ) * 32, minb_bwd(LOGJ)) psf_chain2_
       const int step = p.n_W - m;
       const float* gcur = (step & 1) ? gx1 : gx0;
       float* gnext = (step & 1) ? gx0 : gx1;
-      const float* vprev = p.states + ((long long)(m - 1) * p.B + b) * plane + q * blk;  // V_{m-1}, own block
+      const float* vprev = p.states + ((long long)(m - 1) * NP + bp) * plane + q * blk;  // V_{m-1}, own block
       const float* Wmb = p.W + (long long)(m - 1) * p.sWf + (long long)b * p.sWb;         // sample base
       float* dWmb = p.dW + (long long)(m - 1) * p.sWf + (long long)b * p.sWb;
       const bool last = (m == 1);
@@ -598,8 +612,9 @@ __global__ void __launch_bounds__(nw_bwd(LOGJ) * 32, minb_bwd(LOGJ)) psf_chain2_
             fma4(acc[ch], w, g[ch]);
             fma4(dw, g[ch], vown[ch]);
           }
-          if constexpr (!(kAbl & 2)) st_cs4(dWmb + (long long)k * p.sWt + pos, dw);
-          else if (dw.x == 123.456f) st_cs4(dWmb, dw);
+          if constexpr (!(kAbl & 2)) {
+            if (multi) red_add4g(dWmb + (long long)k * p.sWt + pos, dw); else st_cs4(dWmb + (long long)k * p.sWt + pos, dw);
+          } else if (dw.x == 123.456f) st_cs4(dWmb, dw);
         };
 
         static_for<0, G::NGRP>([&](auto Gi) {
@@ -700,14 +715,26 @@ __global__ void __launch_bounds__(nw_bwd(LOGJ) * 32, minb_bwd(LOGJ)) psf_chain2_
             if constexpr (kAbl & 2) {
               if (dw0.x + dw1.x + dw2.x == 123.456f) st_cs4(d0, dw0);
             } else {
-            st_cs4(d0, dw0);
             float* d1 = dWmb + p.sWt;
-            __stcs(d1 + pos_r0 + 3, dw1.x);
-            st_cs2(d1 + pos_own, dw1.y, dw1.z);
-            __stcs(d1 + pos_own + 2, dw1.w);
             float* d2 = dWmb + 2 * p.sWt;
-            st_cs2(d2 + pos_r0 + 2, dw2.x, dw2.y);
-            st_cs2(d2 + pos_own, dw2.z, dw2.w);
+            if (multi) {
+              red_add4g(d0, dw0);
+              red_add1g(d1 + pos_r0 + 3, dw1.x);
+              red_add1g(d1 + pos_own, dw1.y);
+              red_add1g(d1 + pos_own + 1, dw1.z);
+              red_add1g(d1 + pos_own + 2, dw1.w);
+              red_add1g(d2 + pos_r0 + 2, dw2.x);
+              red_add1g(d2 + pos_r0 + 3, dw2.y);
+              red_add1g(d2 + pos_own, dw2.z);
+              red_add1g(d2 + pos_own + 1, dw2.w);
+            } else {
+              st_cs4(d0, dw0);
+              __stcs(d1 + pos_r0 + 3, dw1.x);
+              st_cs2(d1 + pos_own, dw1.y, dw1.z);
+              __stcs(d1 + pos_own + 2, dw1.w);
+              st_cs2(d2 + pos_r0 + 2, dw2.x, dw2.y);
+              st_cs2(d2 + pos_own, dw2.z, dw2.w);
+            }
             }
             if constexpr (1 < G::NR) issue_R(IC<1>{}); else issue_tail();
           } else {
@@ -723,7 +750,7 @@ __global__ void __launch_bounds__(nw_bwd(LOGJ) * 32, minb_bwd(LOGJ)) psf_chain2_
           for (int ch = 0; ch < CT; ++ch)
             if (!(kAbl & 32) || acc[ch].x == 123.456f) stcg4_keep(gnext + q * blk + ch * J + j, acc[ch], keep);
         } else {
-          store_rows_natural(p.Vout + ((long long)b * n + 4 * (lq * Q + q)) * CT, acc);
+          store_rows_strided(p.Vout + ((long long)b * n + 4 * (lq * Q + q)) * rs + c0, rs, acc);
         }
       }
       if (!last) {
@@ -821,7 +848,7 @@ int resident2(bool bwd, int logj, int logq) {
 int launch2(const void* kernel, const Chain2Params& cp, int logj, int logq, int resident, int threads, cudaStream_t st) {
   const int Q = 1 << logq;
   cudaLaunchConfig_t cfg = {};
-  const int clusters = resident < cp.B ? resident : cp.B;
+  const int clusters = resident < cp.B * cp.G ? resident : cp.B * cp.G;
   cfg.gridDim = dim3((unsigned)(clusters * Q), 1, 1);
   cfg.blockDim = dim3((unsigned)threads, 1, 1);
   cfg.dynamicSmemBytes = (size_t)smem2(logj);
@@ -842,6 +869,7 @@ void fill2(Chain2Params& cp, const PsfChainArgs& a) {
   cp.sWb = a.ws.sample;
   cp.sWt = a.ws.tap;
   cp.B = (int)a.B;
+  cp.G = (int)(a.C / CT);
   cp.n_W = a.n_W;
   cp.residual = a.residual;
   cp.dbg = env_int2("PSF_CHAIN2_DEBUG", 0);
@@ -853,7 +881,7 @@ void fill2(Chain2Params& cp, const PsfChainArgs& a) {
 // not cover it.  Shape rules only; layout/pointer checks are psf_chain2_plan's.
 int psf_chain2_interleave_for(const PsfChainArgs& a) {
   if (env_int2("PSF_CHAIN_V2", 1) == 0) return 0;
-  if (a.C != CT || a.n_W < 1 || a.B < 1 || a.B > (1 << 20)) return 0;
+  if (a.C < CT || a.C % CT != 0 || a.C > 32 * CT || a.n_W < 1 || a.B < 1 || a.B * (a.C / CT) > (1 << 20)) return 0;
   int logn = 0;
   while ((int64_t(1) << logn) < a.n) ++logn;
   if ((int64_t(1) << logn) != a.n || logn < kLogJMin || logn > kLogJBig + 4) return 0;
@@ -877,6 +905,9 @@ int psf_chain2_plan(const PsfChainArgs& a, PsfFusedPlan* plan) {
   const int il = a.interleave < 1 ? 1 : a.interleave;
   if (il != Q) return PSF_ERR_UNSUPPORTED;
   if (a.ws.row != 1 || (a.ws.factor & 3) || (a.ws.sample & 3) || (a.ws.tap & 3)) return PSF_ERR_UNSUPPORTED;
+  // C > 8: the slabs of a sample add into one dW, which is zeroed first as ONE contiguous [n_W][L][B][n] block
+  if (a.C > CT && (a.ws.sample != a.n || a.ws.tap != a.B * a.n || a.ws.factor != (int64_t)a.L * a.B * a.n))
+    return PSF_ERR_UNSUPPORTED;
   int logj, logq;
   geom2(a, Q, &logj, &logq);
   if (!g_attr2_done) {
@@ -941,5 +972,6 @@ int psf_chain2_bwd(const PsfChainArgs& a, const float* W, const float* dOut, flo
   cp.racc = cp.gx + 2 * S;
   cp.save_states = 1;
   fill2(cp, a);
+  if (cp.G > 1) PSF_CUDA_TRY(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)a.n_W * a.L * a.B * a.n, st));
   return launch2(bwd2_kernel_for(logj, logq), cp, logj, logq, plan.resident_bwd, threads2(true, logj), st);
 }

@@ -119,6 +119,33 @@ __device__ __forceinline__ float4 select_quad(const float4& X, const float4& Y, 
 }
 
 // Natural [row][8] <-> per-thread channel planes (4 rows x 8 channels), pure register shuffling.
+// same with a row stride of `rs` floats (C > 8 channels: the 8-channel slab [base, base + 8) of every row)
+__device__ __forceinline__ void load_rows_strided(const float* __restrict__ base, int rs, float4 (&pl)[CT]) {
+  float4 lo[4], hi[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    lo[r] = __ldcs(reinterpret_cast<const float4*>(base + (long long)r * rs));
+    hi[r] = __ldcs(reinterpret_cast<const float4*>(base + (long long)r * rs + 4));
+  }
+  pl[0] = make_float4(lo[0].x, lo[1].x, lo[2].x, lo[3].x);
+  pl[1] = make_float4(lo[0].y, lo[1].y, lo[2].y, lo[3].y);
+  pl[2] = make_float4(lo[0].z, lo[1].z, lo[2].z, lo[3].z);
+  pl[3] = make_float4(lo[0].w, lo[1].w, lo[2].w, lo[3].w);
+  pl[4] = make_float4(hi[0].x, hi[1].x, hi[2].x, hi[3].x);
+  pl[5] = make_float4(hi[0].y, hi[1].y, hi[2].y, hi[3].y);
+  pl[6] = make_float4(hi[0].z, hi[1].z, hi[2].z, hi[3].z);
+  pl[7] = make_float4(hi[0].w, hi[1].w, hi[2].w, hi[3].w);
+}
+__device__ __forceinline__ void store_rows_strided(float* __restrict__ base, int rs, const float4 (&pl)[CT]) {
+  __stcs(reinterpret_cast<float4*>(base), make_float4(pl[0].x, pl[1].x, pl[2].x, pl[3].x));
+  __stcs(reinterpret_cast<float4*>(base + 4), make_float4(pl[4].x, pl[5].x, pl[6].x, pl[7].x));
+  __stcs(reinterpret_cast<float4*>(base + (long long)rs), make_float4(pl[0].y, pl[1].y, pl[2].y, pl[3].y));
+  __stcs(reinterpret_cast<float4*>(base + (long long)rs + 4), make_float4(pl[4].y, pl[5].y, pl[6].y, pl[7].y));
+  __stcs(reinterpret_cast<float4*>(base + 2LL * rs), make_float4(pl[0].z, pl[1].z, pl[2].z, pl[3].z));
+  __stcs(reinterpret_cast<float4*>(base + 2LL * rs + 4), make_float4(pl[4].z, pl[5].z, pl[6].z, pl[7].z));
+  __stcs(reinterpret_cast<float4*>(base + 3LL * rs), make_float4(pl[0].w, pl[1].w, pl[2].w, pl[3].w));
+  __stcs(reinterpret_cast<float4*>(base + 3LL * rs + 4), make_float4(pl[4].w, pl[5].w, pl[6].w, pl[7].w));
+}
 __device__ __forceinline__ void load_rows_natural(const float* __restrict__ base, float4 (&pl)[CT]) {
   float4 lo[4], hi[4];
 #pragma unroll

@@ -67,6 +67,25 @@ def test_gen2_chain_matches_oracle(B, n, residual):
     assert_close(gdW, wdW, "dW")
 
 
+@pytest.mark.parametrize("B,n,C,residual", [
+    (2, 2048, 128, False),    # BASELINE cfg4 chain shape (ListOps-shaped: n = 2048, 128 channels, no residual)
+    (2, 4096, 16, True),      # Q = 2 clusters x 2 slabs
+    (3, 128, 32, True),       # genome-style channel count on the smallest block
+    (1, 16384, 16, True),
+])
+def test_gen2_chain_wide_channels_match_oracle(B, n, C, residual):
+    """C = 8 G channels: every 8-channel slab of a sample runs as its own pseudo-sample on the same W; the slabs'
+    dW contributions meet in a pre-zeroed buffer through red.add (summation order across slabs is not fixed)."""
+    n_W = n.bit_length() - 1
+    W, V0 = make_inputs(B, n, n_W, C, seed=n + C)
+    dOut = torch.randn(B, n, C, generator=torch.Generator().manual_seed(19)) / n
+    want, wdW, wdV = oracle_chain(W, V0, residual, dOut)
+    got, gdW, gdV, _ = run_gen2(W, V0, residual, dOut)
+    assert_close(got, want, "out")
+    assert_close(gdV, wdV, "dV0")
+    assert_close(gdW, wdW, "dW")
+
+
 def test_gen2_no_grad_forward_rotating_slots():
     from sparsefactorization_b200 import chain
     B, n, n_W = 2, 4096, 12
