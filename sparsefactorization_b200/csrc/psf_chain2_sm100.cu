@@ -448,7 +448,7 @@ __global__ void __launch_bounds__(nw_fwd(LOGJ) * 32, minb_fwd(LOGJ)) psf_chain2_
 //   dV_{m-1}[j,:] += W_m[j-o,k] * G_m[j-o,:]      dW_m[j-o,k] = <G_m[j-o,:], V_{m-1}[j,:]>
 // one shifted read of G feeds both; V_{m-1}[j,:] (saved by the forward pass) sits in registers.
 // ---------------------------------------------------------------------------------------------
-template <int LOGJ, int LOGQ>
+template <int LOGJ, int LOGQ, bool kMulti>
 __global__ void __launch_bounds__(nw_bwd(LOGJ) * 32, minb_bwd(LOGJ)) psf_chain2_bwd_kernel(const Chain2Params p) {
   using G = Geo<LOGJ, LOGQ, true>;
   constexpr int J = G::J, Q = G::Q, NQ = G::NQ, kNW = G::NW;
@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(nw_bwd(LOGJ) * 32, minb_bwd(LOGJ)) psf_chain2_
 
   const int NP = p.B * p.G;           // pseudo-samples (sample, 8-channel slab)
   const int rs = CT * p.G;            // floats per row of dOut / dV0
-  const bool multi = p.G > 1;         // several slabs add into the same dW: red.add on a pre-zeroed buffer
+  constexpr bool multi = kMulti;      // G > 1: several slabs add into the same dW: red.add on a pre-zeroed buffer
   for (int bp = cid; bp < NP; bp += ncl) {
     const int b = bp / p.G;
     const int c0 = (bp - b * p.G) * CT;
@@ -613,7 +613,7 @@ __global__ void __launch_bounds__(nw_bwd(LOGJ) * 32, minb_bwd(LOGJ)) psf_chain2_
             fma4(dw, g[ch], vown[ch]);
           }
           if constexpr (!(kAbl & 2)) {
-            if (multi) red_add4g(dWmb + (long long)k * p.sWt + pos, dw); else st_cs4(dWmb + (long long)k * p.sWt + pos, dw);
+            if constexpr (multi) red_add4g(dWmb + (long long)k * p.sWt + pos, dw); else st_cs4(dWmb + (long long)k * p.sWt + pos, dw);
           } else if (dw.x == 123.456f) st_cs4(dWmb, dw);
         };
 
@@ -717,7 +717,7 @@ __global__ void __launch_bounds__(nw_bwd(LOGJ) * 32, minb_bwd(LOGJ)) psf_chain2_
             } else {
             float* d1 = dWmb + p.sWt;
             float* d2 = dWmb + 2 * p.sWt;
-            if (multi) {
+            if constexpr (multi) {
               red_add4g(d0, dw0);
               red_add1g(d1 + pos_r0 + 3, dw1.x);
               red_add1g(d1 + pos_own, dw1.y);
@@ -804,8 +804,27 @@ int env_int2(const char* name, int dflt) {
     case 2: return (const void*)K<kLogJ, 2>;                            \
     default: return (const void*)K<kLogJ, 3>;                           \
   }
+template <int LJ, int LQ>
+struct Bwd1 { static const void* get() { return (const void*)psf_chain2_bwd_kernel<LJ, LQ, false>; } };
+template <int LJ, int LQ>
+struct BwdM { static const void* get() { return (const void*)psf_chain2_bwd_kernel<LJ, LQ, true>; } };
+#define PSF2_STRUCT_CASES(S)                                            \
+  if (logj == 7) return S<7, 0>::get();                                 \
+  if (logj == 8) return S<8, 0>::get();                                 \
+  if (logj == 9) return S<9, 0>::get();                                 \
+  if (logj == 10) return S<10, 0>::get();                               \
+  if (logj == 12) return logq == 3 ? S<12, 3>::get() : S<12, 4>::get(); \
+  switch (logq) {                                                       \
+    case 0: return S<kLogJ, 0>::get();                                  \
+    case 1: return S<kLogJ, 1>::get();                                  \
+    case 2: return S<kLogJ, 2>::get();                                  \
+    default: return S<kLogJ, 3>::get();                                 \
+  }
 const void* fwd2_kernel_for(int logj, int logq) { PSF2_KERNEL_CASES(psf_chain2_fwd_kernel) }
-const void* bwd2_kernel_for(int logj, int logq) { PSF2_KERNEL_CASES(psf_chain2_bwd_kernel) }
+const void* bwd2_kernel_for(int logj, int logq, bool multi = false) {
+  if (multi) { PSF2_STRUCT_CASES(BwdM) }
+  PSF2_STRUCT_CASES(Bwd1)
+}
 
 int smem2(int logj) { return CT * (1 << logj) * 4 + 64; }
 int threads2(bool bwd, int logj) { return (bwd ? nw_bwd(logj) : nw_fwd(logj)) * 32; }
@@ -833,7 +852,9 @@ int resident2(bool bwd, int logj, int logq) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int ncl = 0;
-  if (Q > 8 && cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+  if (Q > 8 && (cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+                (bwd && cudaFuncSetAttribute(bwd2_kernel_for(logj, logq, true), cudaFuncAttributeNonPortableClusterSizeAllowed,
+                                             1) != cudaSuccess))) {
     cudaGetLastError();
     return 0;
   }
@@ -915,7 +936,9 @@ int psf_chain2_plan(const PsfChainArgs& a, PsfFusedPlan* plan) {
       for (int lq = (lj == kLogJBig ? 3 : 0); lq < (lj == kLogJBig ? 5 : (lj == kLogJ ? 4 : 1)); ++lq)
         if (cudaFuncSetAttribute(fwd2_kernel_for(lj, lq), cudaFuncAttributeMaxDynamicSharedMemorySize, smem2(lj)) !=
                 cudaSuccess ||
-            cudaFuncSetAttribute(bwd2_kernel_for(lj, lq), cudaFuncAttributeMaxDynamicSharedMemorySize, smem2(lj)) !=
+            cudaFuncSetAttribute(bwd2_kernel_for(lj, lq, false), cudaFuncAttributeMaxDynamicSharedMemorySize, smem2(lj)) !=
+                cudaSuccess ||
+            cudaFuncSetAttribute(bwd2_kernel_for(lj, lq, true), cudaFuncAttributeMaxDynamicSharedMemorySize, smem2(lj)) !=
                 cudaSuccess) {
           cudaGetLastError();
           return PSF_ERR_UNSUPPORTED;
@@ -973,5 +996,5 @@ int psf_chain2_bwd(const PsfChainArgs& a, const float* W, const float* dOut, flo
   cp.save_states = 1;
   fill2(cp, a);
   if (cp.G > 1) PSF_CUDA_TRY(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)a.n_W * a.L * a.B * a.n, st));
-  return launch2(bwd2_kernel_for(logj, logq), cp, logj, logq, plan.resident_bwd, threads2(true, logj), st);
+  return launch2(bwd2_kernel_for(logj, logq, cp.G > 1), cp, logj, logq, plan.resident_bwd, threads2(true, logj), st);
 }

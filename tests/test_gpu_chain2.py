@@ -72,6 +72,7 @@ def test_gen2_chain_matches_oracle(B, n, residual):
     (2, 4096, 16, True),      # Q = 2 clusters x 2 slabs
     (3, 128, 32, True),       # genome-style channel count on the smallest block
     (1, 16384, 16, True),
+    (1, 65536, 16, False),    # 16-CTA clusters x 2 slabs
 ])
 def test_gen2_chain_wide_channels_match_oracle(B, n, C, residual):
     """C = 8 G channels: every 8-channel slab of a sample runs as its own pseudo-sample on the same W; the slabs'
