@@ -1,5 +1,7 @@
-// Fused chord-factor chain, second generation ("quad-interleaved clusters"), sm_100a, fp32, C = 8,
-// n = 2^p rows with the standard chord offsets 0,1,2,4,...,n/2 (L = p+1 taps).
+// Fused chord-factor chain, second generation ("quad-interleaved clusters"), sm_100a, fp32, C = 8 G channels
+// (each 8-channel slab of a sample is processed like a sample of its own), n = 2^p rows, p = 7 .. 16, with the
+// standard chord offsets 0,1,2,4,...,n/2 (L = p+1 taps).  The description below is for the tuned shape
+// J = 2048 (n = 2048 .. 16384); smaller n use one CTA per sample, n = 32768 / 65536 use J = 4096.
 //
 // One cluster of Q = n/J CTAs owns one sample (J = 2048 rows per CTA).  Unlike the first generation
 // (psf_chain_sm100.cu: contiguous row blocks), CTA q owns the row QUADS u = i>>2 with u mod Q == q:
