@@ -214,6 +214,7 @@ __device__ __forceinline__ void stcg4_keep(float* p, const float4& v, unsigned l
                : "memory");
 }
 
+#if PSF2_TMEM_RACC
 // ---- tensor memory as per-thread scratch (32 columns = one quad set of 8 channels) ------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst_u32, uint32_t ncols) {  // one warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst_u32), "r"(ncols) : "memory");
@@ -245,6 +246,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float4 (&v)[CT]) {
       : "r"(taddr)
       : "memory");
 }
+
+#endif
 
 __device__ __forceinline__ void red_add4g(float* p, const float4& v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");

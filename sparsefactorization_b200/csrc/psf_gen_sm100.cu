@@ -30,6 +30,10 @@ constexpr int GLP = 16;   // taps padded
 constexpr int kBlkFwd = GH * GE + GH + GH * GLP + GLP;  // w1[h][e], b1[h], w2t[h][l], b2[l]  = 1584 floats
 constexpr int kBlkBwd = GH * GE + GH + GLP * GH;        // w1[h][e], b1[h], w2[l][h]          = 1568 floats
 constexpr int kAccBlk = GH * GE + GH + GLP * GH + GLP;  // dW1, db1, dW2 (l-major, padded), db2 = 1584 floats
+#ifndef PSF_GEN_P2_UNROLL
+#define PSF_GEN_P2_UNROLL 2
+#endif
+constexpr int kP2Unroll = PSF_GEN_P2_UNROLL;  // unrolling of the phase-2 row loops of the backward kernel
 constexpr int XS = GE + 4;                               // padded row stride of the staged tiles (bank-conflict free)
 constexpr int DS = GLP + 4;
 
@@ -447,7 +451,7 @@ __global__ void __launch_bounds__(kTB, 384 / kTB) psf_gen_bwd_kernel(const GenPa
         for (int i = 0; i < 32; ++i) v[i] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) db[i] = 0.f;
-#pragma unroll 1
+#pragma unroll kP2Unroll
         for (int rr = 0; rr < kTB / KG1; ++rr) {
           const int r = rr * KG1 + kg;
           const float4 d0 = lds4g(dps + r * XS + hb * 8), d1 = lds4g(dps + r * XS + hb * 8 + 4);
@@ -504,7 +508,7 @@ __global__ void __launch_bounds__(kTB, 384 / kTB) psf_gen_bwd_kernel(const GenPa
         for (int i = 0; i < 32; ++i) v[i] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) db[i] = 0.f;
-#pragma unroll 1
+#pragma unroll kP2Unroll
         for (int rr = 0; rr < kTB / KG2; ++rr) {
           const int r = rr * KG2 + kg;
           const float4 d0 = lds4g(dos + r * DS + lb * 8), d1 = lds4g(dos + r * DS + lb * 8 + 4);
