@@ -297,6 +297,17 @@ class PSFChainMixin:
             V = v_dropout(V)
         return chord_chain(W, V, use_residuals=self.use_residuals, interleave=Q)
 
+    @torch.no_grad()
+    def attention_map(self, data: torch.Tensor) -> torch.Tensor:
+        """Dense ``[B, n, n]`` product of the factors generated from the embedded ``data`` ``[B, n, E]`` (what
+        ChangedPSF.forward returns as ``W_final``, LRA/attention_maps/imdb_inference.py:24-69)."""
+        from .chain import attention_map as _amap
+        n_W, (B, n, _) = len(self.fs), data.shape
+        L = self.fs[0].network[-1].out_features
+        homog = _same_structure(self.fs)
+        Q = preferred_interleave(n_W, B, n, L, n) if data.dtype == torch.float32 and homog and n % 8 == 0 else 1
+        return _amap(generate_factors(self.fs, data, Q), interleave=Q)
+
     def _apply_chain(self, data: torch.Tensor, V: torch.Tensor) -> torch.Tensor:
         n_W, (B, n, _) = len(self.fs), data.shape
         L = self.fs[0].network[-1].out_features

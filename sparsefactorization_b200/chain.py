@@ -188,6 +188,18 @@ def chord_chain(W: torch.Tensor, V0: torch.Tensor, use_residuals: bool = False,
     return _ChordChainFn.apply(W, V0, bool(use_residuals), offsets, path, int(interleave))
 
 
+def attention_map(W: torch.Tensor, offsets: Optional[Sequence[int]] = None, path: str = "auto",
+                  interleave: int = 1) -> torch.Tensor:
+    """Dense ``[B, n, n]`` matrix ``W[n_W-1] ... W[0]`` of every sample: the chain applied to the identity, as the
+    reference's attention-map scripts build it (``W_final = spmm(..., W_final)`` starting from ``torch.eye(n)``,
+    LRA/attention_maps/imdb_inference.py:41-59, pathfinder_inference.py:57-81).  No residual, no gradient.
+    ``out[b] @ V0[b]`` equals ``chord_chain(W, V0)[b]``.  The fused kernels treat it as ``C = n`` channels."""
+    n_W, B, n, L = W.shape
+    eye = torch.eye(n, dtype=W.dtype, device=W.device).expand(B, n, n).contiguous()
+    with torch.no_grad():
+        return chord_chain(W.detach(), eye, False, offsets, path, interleave)
+
+
 def empty_tap_major(n_W: int, B: int, n: int, L: int, dtype=torch.float32, device="cuda") -> torch.Tensor:
     """Logical ``[n_W, B, n, L]`` view of a physical ``[n_W, L, B, n]`` buffer (row stride 1)."""
     return torch.empty(n_W, L, B, n, dtype=dtype, device=device).permute(0, 2, 3, 1)

@@ -907,7 +907,8 @@ void fill2(Chain2Params& cp, const PsfChainArgs& a) {
 // not cover it.  Shape rules only; layout/pointer checks are psf_chain2_plan's.
 int psf_chain2_interleave_for(const PsfChainArgs& a) {
   if (env_int2("PSF_CHAIN_V2", 1) == 0) return 0;
-  if (a.C < CT || a.C % CT != 0 || a.C > 32 * CT || a.n_W < 1 || a.B < 1 || a.B * (a.C / CT) > (1 << 20)) return 0;
+  // up to 65536 channels: the dense attention map (chain applied to the n x n identity) is C = n
+  if (a.C < CT || a.C % CT != 0 || a.C > 65536 || a.n_W < 1 || a.B < 1 || a.B * (a.C / CT) > (1 << 20)) return 0;
   int logn = 0;
   while ((int64_t(1) << logn) < a.n) ++logn;
   if ((int64_t(1) << logn) != a.n || logn < kLogJMin || logn > kLogJBig + 4) return 0;

@@ -93,14 +93,28 @@ class PSFNet(PSFChainMixin, nn.Module):
         self.embedding.weight.data.uniform_(-initrange, initrange)
         self.embedding.weight.requires_grad = True
 
-    def forward(self, data):
+    def _embed(self, data):
         data = self.embedding(data)
         if self.use_pos_embedding:
             positions = torch.arange(0, self.n_vec, device=data.device).expand(data.size(0), self.n_vec)
             data = data + self.pos_embedding(positions)
-        data = self.dropout1(data)
+        return self.dropout1(data)
+
+    def forward(self, data):
+        data = self._embed(data)
         V = self._chain_from_data(data, self.dropout2)   # V = dropout2(g(data)), then the factor chain
         V = self.dropout3(V)
         if self.pooling_type == 'CLS':
             V = V[:, 0, :]
         return self.final(V.reshape(V.size(0), -1))
+
+    def forward_with_attention_map(self, data):
+        """``(logits, W_final)`` like ``ChangedPSF.forward`` of the reference's attention-map scripts
+        (LRA/attention_maps/imdb_inference.py:24-69): W_final is the dense ``[B, n, n]`` product of the factors.
+        Inference helper: call it in eval mode (the factors of the map and of the logits then see the same input)."""
+        emb = self._embed(data)
+        V = self._chain_from_data(emb, self.dropout2)
+        V = self.dropout3(V)
+        if self.pooling_type == 'CLS':
+            V = V[:, 0, :]
+        return self.final(V.reshape(V.size(0), -1)), self.attention_map(emb)

@@ -87,6 +87,41 @@ def test_gen2_chain_wide_channels_match_oracle(B, n, C, residual):
     assert_close(gdW, wdW, "dW")
 
 
+@pytest.mark.parametrize("n_W", [1, 2, 3])
+@pytest.mark.parametrize("n", [512, 4096])
+def test_gen2_short_chains(n, n_W):
+    """Fewer factors than log2(n) (the taps still are the full chord set): first/last-factor special cases and the
+    every-other-factor residual accumulation with odd and even chain lengths."""
+    L = n.bit_length()
+    W, V0 = make_inputs(2, n, n_W, 8, seed=n + n_W, L=L)
+    dOut = torch.randn(2, n, 8, generator=torch.Generator().manual_seed(23)) / n
+    want, wdW, wdV = oracle_chain(W, V0, True, dOut)
+    got, gdW, gdV, _ = run_gen2(W, V0, True, dOut)
+    assert_close(got, want, "out")
+    assert_close(gdV, wdV, "dV0")
+    assert_close(gdW, wdW, "dW")
+
+
+@pytest.mark.parametrize("B,n", [(2, 256), (1, 1024), (1, 4096)])
+def test_attention_map_is_the_dense_chain(B, n):
+    """chain applied to the identity (C = n channels through the fused kernels) against the oracle's loop, and
+    against its defining property  map @ V0 == chain(V0)."""
+    from sparsefactorization_b200 import chain
+    n_W = n.bit_length() - 1
+    W, V0 = make_inputs(B, n, n_W, 8, seed=3 * n)
+    Q = chain.preferred_interleave(n_W, B, n, n_W + 1, n)
+    Wd = chain.to_tap_major(W.to(dev()), interleave=Q)
+    amap = chain.attention_map(Wd, interleave=Q)
+    assert amap.shape == (B, n, n) and chain.last_path_used == "fused"
+    if n <= 1024:
+        idx = torch.tensor(oracle.get_chord_indices_assym(n, n_W + 1))
+        want = oracle.chain_ref(idx, [W[m] for m in range(n_W)], torch.eye(n).expand(B, n, n).contiguous(), n, False)
+        assert_close(amap.cpu(), want, "attention map")
+    with torch.no_grad():
+        out = chain.chord_chain(Wd, V0.to(dev()), False, interleave=Q)
+    torch.testing.assert_close(torch.bmm(amap, V0.to(dev())), out, rtol=1e-4, atol=1e-5)
+
+
 def test_gen2_no_grad_forward_rotating_slots():
     from sparsefactorization_b200 import chain
     B, n, n_W = 2, 4096, 12

@@ -223,3 +223,23 @@ def test_fused_generators_with_v_generator(B, n, n_W, L, C, Q, save_pre, monkeyp
     for (name, p32), p64 in zip(list(fs.named_parameters()) + [("g." + k, v) for k, v in g.named_parameters()],
                                 mods64.parameters()):
         close(p32.grad, p64.grad, name)
+
+
+def test_lra_forward_with_attention_map():
+    """(logits, W_final) of the inference helper: logits equal forward(); the map applied to V0 = g(embedded data)
+    reproduces the chain output the head sees (no residual in the LRA configs)."""
+    from sparsefactorization_b200.lra.psf import PSFNet
+    torch.manual_seed(3)
+    n, n_W = 256, 8
+    net = PSFNet(vocab_size=17, embedding_size=32, n_vec=n, n_W=n_W, Ws=[32, "GELU"], V=[32, "GELU"], n_channels_V=8,
+                 n_class=10, pooling_type="FLATTEN", head=["linear"], use_cuda=True, use_residuals=False,
+                 dropout1_p=0.1, dropout2_p=0.1, dropout3_p=0.1, init_embedding_weights=False, use_pos_embedding=True,
+                 problem="listops").cuda().eval()
+    X = torch.randint(0, 15, (3, n), device="cuda")
+    with torch.no_grad():
+        logits, amap = net.forward_with_attention_map(X)
+        assert amap.shape == (3, n, n)
+        torch.testing.assert_close(logits, net(X), rtol=1e-6, atol=1e-6)
+        emb = net._embed(X)
+        V = torch.bmm(amap, net.g(emb))
+        torch.testing.assert_close(net.final(V.reshape(3, -1)), logits, rtol=1e-4, atol=1e-5)
