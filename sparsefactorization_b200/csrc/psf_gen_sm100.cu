@@ -30,6 +30,10 @@ constexpr int GLP = 16;   // taps padded
 constexpr int kBlkFwd = GH * GE + GH + GH * GLP + GLP;  // w1[h][e], b1[h], w2t[h][l], b2[l]  = 1584 floats
 constexpr int kBlkBwd = GH * GE + GH + GLP * GH;        // w1[h][e], b1[h], w2[l][h]          = 1568 floats
 constexpr int kAccBlk = GH * GE + GH + GLP * GH + GLP;  // dW1, db1, dW2 (l-major, padded), db2 = 1584 floats
+// phase 2 of the backward kernel (parameter-gradient GEMMs): 1 = tensor cores (mma.sync 3xTF32), 0 = FP32 FMA tiles
+#ifndef PSF_GEN_MMA
+#define PSF_GEN_MMA 1
+#endif
 #ifndef PSF_GEN_P2_UNROLL
 #define PSF_GEN_P2_UNROLL 2
 #endif
@@ -74,6 +78,21 @@ __device__ __forceinline__ void red_add4(float* p, float a, float b, float c, fl
 }
 __device__ __forceinline__ void red_add1(float* p, float a) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
+}
+__device__ __forceinline__ void red_add2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+// v = hi + lo with hi, lo representable in TF32 (10-bit mantissa): the operand split of the 3xTF32 scheme
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
+  const float rest = v - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(rest));
+}
+// D(16x8) += A(16x8, row) * B(8x8, col), TF32 inputs, fp32 accumulate (warp-level tensor-core instruction)
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -440,6 +459,115 @@ __global__ void __launch_bounds__(kTB, 384 / kTB) psf_gen_bwd_kernel(const GenPa
       cp_async_commit();
 
       float* acc_m = wsc + (long long)m * kAccBlk;
+#if PSF_GEN_MMA
+      // ---- phase 2 on the tensor cores: the two parameter-gradient GEMMs (K = rows) as warp-level
+      //      mma.sync.m16n8k8 TF32 with error compensation (3xTF32: a = a_hi + a_lo, a b ~ a_lo b_hi + a_hi b_lo +
+      //      a_hi b_hi, fp32 accumulate; relative error ~1e-6, gradients only).  Every warp multiplies the 32 rows it
+      //      staged itself; the warps' partial 32x32 / 16x32 results are summed through shared memory (fixed order)
+      //      and added to the CTA's accumulator slice with one red.add per four elements. ------------------------
+      {
+        const int g = lane >> 2, t = lane & 3;
+        const int r0 = warp * 32;
+        // dW1[h][e] += dpre^T x:  M = h (2 tiles of 16), N = e (4 tiles of 8), K = this warp's rows (4 steps of 8)
+        float d1[2][4][4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) d1[i][j][k] = 0.f;
+        // dW2[l][h] += dout^T hid:  M = l (16), N = h (4 tiles of 8)
+        float d2[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) d2[j][k] = 0.f;
+#pragma unroll 1
+        for (int ks = 0; ks < 4; ++ks) {
+          const int ra = (r0 + ks * 8 + t) * XS, rb = ra + 4 * XS;          // rows k = t and k = t + 4 of this step
+          uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {                                    // B = x[k][e]
+            split_tf32(xs[ra + nt * 8 + g], bh[nt][0], bl[nt][0]);
+            split_tf32(xs[rb + nt * 8 + g], bh[nt][1], bl[nt][1]);
+          }
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {                                    // A = dpre[k][h]^T
+            uint32_t ah[4], al[4];
+            split_tf32(dps[ra + mt * 16 + g], ah[0], al[0]);
+            split_tf32(dps[ra + mt * 16 + g + 8], ah[1], al[1]);
+            split_tf32(dps[rb + mt * 16 + g], ah[2], al[2]);
+            split_tf32(dps[rb + mt * 16 + g + 8], ah[3], al[3]);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+              mma_tf32(d1[mt][nt], al, bh[nt]);
+              mma_tf32(d1[mt][nt], ah, bl[nt]);
+              mma_tf32(d1[mt][nt], ah, bh[nt]);
+            }
+          }
+          const int da = (r0 + ks * 8 + t) * DS, db_ = da + 4 * DS;
+          uint32_t ah[4], al[4];                                              // A = dout[k][l]^T
+          split_tf32(dos[da + g], ah[0], al[0]);
+          split_tf32(dos[da + g + 8], ah[1], al[1]);
+          split_tf32(dos[db_ + g], ah[2], al[2]);
+          split_tf32(dos[db_ + g + 8], ah[3], al[3]);
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {                                    // B = hid[k][h]
+            uint32_t hh[2], hl[2];
+            split_tf32(hs[ra + nt * 8 + g], hh[0], hl[0]);
+            split_tf32(hs[rb + nt * 8 + g], hh[1], hl[1]);
+            mma_tf32(d2[nt], al, hh);
+            mma_tf32(d2[nt], ah, hl);
+            mma_tf32(d2[nt], ah, hh);
+          }
+        }
+        // bias gradients: column sums over this warp's rows (lane = column)
+        float sb1 = 0.f, sb2 = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+          sb1 += dps[(r0 + r) * XS + lane];
+          sb2 += dos[(r0 + r) * DS + (lane & (GLP - 1))];
+        }
+        red_add1(acc_m + GH * GE + lane, sb1);
+        if (lane < GLP) red_add1(acc_m + GH * GE + GH + GLP * GH + lane, sb2);
+        // cross-warp reduction through shared memory (the dpre / hid tiles are dead once every warp is here):
+        // partial[warp][48 rows: 32 of dW1, 16 of dW2][PS], then one red.add.v4 per 4 elements of the CTA's sums
+        constexpr int PS = 40;                       // padded row: the fragment stores are at most 2-way conflicted
+        float* part = dps;                           // dps and hs are contiguous: 2 * kTB * XS >= (kTB / 32) * 48 * PS
+        static_assert(2 * kTB * XS >= (kTB / 32) * 48 * PS, "partial sums do not fit the dead tiles");
+        __syncthreads();
+        float* mine = part + warp * 48 * PS;
+        // accumulator fragments: c0 (g, 2t), c1 (g, 2t+1), c2 (g+8, 2t), c3 (g+8, 2t+1)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            *reinterpret_cast<float2*>(mine + (mt * 16 + g) * PS + nt * 8 + 2 * t) = make_float2(d1[mt][nt][0], d1[mt][nt][1]);
+            *reinterpret_cast<float2*>(mine + (mt * 16 + g + 8) * PS + nt * 8 + 2 * t) = make_float2(d1[mt][nt][2], d1[mt][nt][3]);
+          }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          *reinterpret_cast<float2*>(mine + (32 + g) * PS + nt * 8 + 2 * t) = make_float2(d2[nt][0], d2[nt][1]);
+          *reinterpret_cast<float2*>(mine + (32 + g + 8) * PS + nt * 8 + 2 * t) = make_float2(d2[nt][2], d2[nt][3]);
+        }
+        __syncthreads();
+        for (int u = tid; u < 48 * 8; u += kTB) {    // float4 units: row u / 8, columns 4 (u % 8) ..
+          const int row = u >> 3, col = (u & 7) * 4;
+          float4 sum = lds4g(part + row * PS + col);
+#pragma unroll
+          for (int w = 1; w < kTB / 32; ++w) {
+            const float4 v = lds4g(part + (w * 48 + row) * PS + col);
+            sum.x += v.x;
+            sum.y += v.y;
+            sum.z += v.z;
+            sum.w += v.w;
+          }
+          // rows 0..31 are dW1[h][e]; rows 32..47 are dW2[l][h], stored after dW1 and db1 in the accumulator block
+          float* dst = row < 32 ? acc_m + row * GE + col : acc_m + GH * GE + GH + (row - 32) * GH + col;
+          red_add4(dst, sum.x, sum.y, sum.z, sum.w);
+        }
+      }
+#else
       // ---- phase 2a: dW1[h][e] += sum_rows dpre[row][h] * x[row][e]  (+ db1) -----------------
       {
         const int kg = lane & (KG1 - 1);                            // row group: rows rr*KG1 + kg
@@ -553,6 +681,7 @@ __global__ void __launch_bounds__(kTB, 384 / kTB) psf_gen_bwd_kernel(const GenPa
           if (hb == 0) red_add1(acc_m + GH * GE + GH + GLP * GH + lb * 8 + i, db[0]);
         }
       }
+#endif
     }
     if (live) {
       float4* dst = reinterpret_cast<float4*>(p.dx + row * GE);
