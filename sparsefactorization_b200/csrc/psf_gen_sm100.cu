@@ -34,6 +34,11 @@ constexpr int kAccBlk = GH * GE + GH + GLP * GH + GLP;  // dW1, db1, dW2 (l-majo
 #ifndef PSF_GEN_MMA
 #define PSF_GEN_MMA 1
 #endif
+// 1: the whole backward pass on tensor cores (psf_gen_bwd_mma_kernel); 0: phase 1 in FP32 FMA (psf_gen_bwd_kernel)
+#ifndef PSF_GEN_BWD_ALL_MMA
+#define PSF_GEN_BWD_ALL_MMA 1
+#endif
+constexpr bool kBwdAllMma = PSF_GEN_BWD_ALL_MMA != 0;
 #ifndef PSF_GEN_P2_UNROLL
 #define PSF_GEN_P2_UNROLL 2
 #endif
@@ -83,10 +88,10 @@ __device__ __forceinline__ void red_add2(float* p, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
 }
 // v = hi + lo with hi, lo representable in TF32 (10-bit mantissa): the operand split of the 3xTF32 scheme
+// (truncating split: hi = upper 19 bits, lo = v - hi exactly; the tensor core ignores the low 13 mantissa bits of lo)
 __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
-  const float rest = v - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(rest));
+  hi = __float_as_uint(v) & 0xffffe000u;
+  lo = __float_as_uint(v - __uint_as_float(hi));
 }
 // D(16x8) += A(16x8, row) * B(8x8, col), TF32 inputs, fp32 accumulate (warp-level tensor-core instruction)
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
@@ -691,6 +696,302 @@ __global__ void __launch_bounds__(kTB, 384 / kTB) psf_gen_bwd_kernel(const GenPa
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// backward, tensor-core version: every GEMM-shaped piece of the backward pass runs as warp-level
+// mma.sync.m16n8k8 TF32 with 3xTF32 error compensation (gradients only; relative error ~1e-6):
+//   pre  [rows x h] = x    [rows x e] W1^T      dhid [rows x h] = dout [rows x l] W2
+//   dx   [rows x e] += dpre[rows x h] W1        dW1 += dpre^T x,  dW2 += dout^T hid   (K = rows)
+// A warp owns 32 rows of the 128-row tile for all of them, so the only CTA-wide synchronisation is the weight
+// staging and the cross-warp sum of the parameter-gradient partials.  pre and dhid come out in the same
+// accumulator-fragment layout, so gelu / gelu' / dpre are elementwise on registers.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMT = 128;                                  // rows per tile == threads per CTA
+constexpr int kWP = GE + 4;                               // padded weight row (conflict-free B-fragment loads)
+constexpr int kBlkMma = GH * kWP + GH + GLP * kWP;        // w1p[h][e], b1[h], w2p[l][h]
+constexpr int kSmemBwdMma = (3 * kMT * XS + kMT * DS + kBlkMma) * 4;
+
+__global__ void __launch_bounds__(kMT, 3) psf_gen_bwd_mma_kernel(const GenParams p) {
+  extern __shared__ __align__(16) float gsm[];
+  float* xs = gsm;                  // [kMT][XS]  x rows of the tile
+  float* dps = xs + kMT * XS;       // [kMT][XS]  dpre
+  float* hs = dps + kMT * XS;       // [kMT][XS]  hidden activations
+  float* dos = hs + kMT * XS;       // [kMT][DS]  dout (taps padded with zeros)
+  float* wb = dos + kMT * DS;       // weights of the current generator
+  const float* w1 = wb;             // [GH][kWP]
+  const float* b1 = wb + GH * kWP;  // [GH]
+  const float* w2 = b1 + GH;        // [GLP][kWP], rows >= Lm are zero
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int r0 = warp * 32;
+  float* wsc = p.ws + (long long)blockIdx.x * p.n_gen * kAccBlk;
+  const long long ntiles = (p.rows + kMT - 1) / kMT;
+
+  auto request_weights = [&](int m) {   // 16-byte cp.async pieces into padded rows
+    const float *W1, *b1g, *W2, *b2g;
+    int Lm;
+    gen_ptrs(p, m, W1, b1g, W2, b2g, Lm);
+    for (int c = tid; c < GH * 8; c += kMT) cp_async16(wb + (c >> 3) * kWP + 4 * (c & 7), W1 + 4 * c);
+    if (tid < GH / 4) cp_async16(wb + GH * kWP + 4 * tid, b1g + 4 * tid);
+    float* w2d = wb + GH * kWP + GH;
+    for (int c = tid; c < GLP * 8; c += kMT) {
+      const int l = c >> 3;
+      if (l < Lm) cp_async16(w2d + l * kWP + 4 * (c & 7), W2 + 4 * c);
+      else *reinterpret_cast<float4*>(w2d + l * kWP + 4 * (c & 7)) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row = tile * kMT + tid;
+    const bool live = row < p.rows;
+    {
+      float4 xin[GE / 4];
+#pragma unroll
+      for (int i = 0; i < GE / 4; ++i)
+        xin[i] = live ? __ldg(reinterpret_cast<const float4*>(p.x + row * GE) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncthreads();  // the previous tile is completely done with the staged tiles and the weights
+#pragma unroll
+      for (int i = 0; i < GE / 4; ++i) *reinterpret_cast<float4*>(xs + tid * XS + 4 * i) = xin[i];
+    }
+    request_weights(0);
+    cp_async_commit();
+    const long long nat = (live && p.n_gen > p.n_W) ? natural_row(p, row) : 0;
+    auto load_dout = [&](int mm, float (&d)[GLP]) {
+      if (mm < p.n_W) {
+        const float* src = p.Wt + (long long)mm * p.sWf + row;
+#pragma unroll
+        for (int l = 0; l < GLP; ++l) d[l] = (live && l < p.L) ? __ldcs(src + (long long)l * p.sWt) : 0.f;
+      } else {
+        const float* src = p.V + nat * p.C;
+#pragma unroll
+        for (int c = 0; c < GLP; ++c) d[c] = (live && c < p.C) ? __ldcs(src + c) : 0.f;
+      }
+    };
+    float dnext[GLP];
+    load_dout(0, dnext);
+    float dxa[2][4][4];   // dx fragments of this warp's rows: [16-row tile][8-column tile][c0..c3]
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dxa[i][j][k] = 0.f;
+
+#pragma unroll 1
+    for (int m = 0; m < p.n_gen; ++m) {
+      __syncthreads();  // the reduction of the previous generator has finished reading the partials in dps / hs
+#pragma unroll
+      for (int i = 0; i < GLP / 4; ++i)
+        *reinterpret_cast<float4*>(dos + tid * DS + 4 * i) =
+            make_float4(dnext[4 * i], dnext[4 * i + 1], dnext[4 * i + 2], dnext[4 * i + 3]);
+      if (m + 1 < p.n_gen) load_dout(m + 1, dnext);   // streamed from HBM: a whole generator ahead
+      cp_async_wait<0>();
+      __syncthreads();  // weights, dout (and x) are visible
+
+      // ---- phase 1: pre = x W1^T, dhid = dout W2, gelu / gelu' / dpre elementwise, stage hid and dpre ----
+#pragma unroll 1
+      for (int mt = 0; mt < 2; ++mt) {
+        const int ra = (r0 + 16 * mt + g) * XS, rb = ra + 8 * XS;
+        uint32_t xh[4][4], xl[4][4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          split_tf32(xs[ra + 8 * ks + t], xh[ks][0], xl[ks][0]);
+          split_tf32(xs[rb + 8 * ks + t], xh[ks][1], xl[ks][1]);
+          split_tf32(xs[ra + 8 * ks + t + 4], xh[ks][2], xl[ks][2]);
+          split_tf32(xs[rb + 8 * ks + t + 4], xh[ks][3], xl[ks][3]);
+        }
+        const int da = (r0 + 16 * mt + g) * DS, db_ = da + 8 * DS;
+        uint32_t oh[2][4], ol[2][4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          split_tf32(dos[da + 8 * ks + t], oh[ks][0], ol[ks][0]);
+          split_tf32(dos[db_ + 8 * ks + t], oh[ks][1], ol[ks][1]);
+          split_tf32(dos[da + 8 * ks + t + 4], oh[ks][2], ol[ks][2]);
+          split_tf32(dos[db_ + 8 * ks + t + 4], oh[ks][3], ol[ks][3]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const float bia0 = b1[8 * nt + 2 * t], bia1 = b1[8 * nt + 2 * t + 1];
+          float pre[4] = {bia0, bia1, bia0, bia1};
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {   // B[k = e][n = h] = W1[h][e]
+            uint32_t bh[2], bl[2];
+            split_tf32(w1[(8 * nt + g) * kWP + 8 * ks + t], bh[0], bl[0]);
+            split_tf32(w1[(8 * nt + g) * kWP + 8 * ks + t + 4], bh[1], bl[1]);
+            mma_tf32(pre, xl[ks], bh);
+            mma_tf32(pre, xh[ks], bl);
+            mma_tf32(pre, xh[ks], bh);
+          }
+          float dh[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {   // B[k = l][n = h] = W2[l][h]
+            uint32_t bh[2], bl[2];
+            split_tf32(w2[(8 * ks + t) * kWP + 8 * nt + g], bh[0], bl[0]);
+            split_tf32(w2[(8 * ks + t + 4) * kWP + 8 * nt + g], bh[1], bl[1]);
+            mma_tf32(dh, ol[ks], bh);
+            mma_tf32(dh, oh[ks], bl);
+            mma_tf32(dh, oh[ks], bh);
+          }
+          float hid[4], dpre[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float cdf, pdf;
+            normal_cdf_pdf_fast(pre[i], cdf, pdf);
+            hid[i] = pre[i] * cdf;
+            dpre[i] = dh[i] * (cdf + pre[i] * pdf);
+          }
+          // fragment (c0, c1) = row g, columns 2t, 2t+1 of the 8-column tile; (c2, c3) = row g + 8
+          *reinterpret_cast<float2*>(hs + ra + 8 * nt + 2 * t) = make_float2(hid[0], hid[1]);
+          *reinterpret_cast<float2*>(hs + rb + 8 * nt + 2 * t) = make_float2(hid[2], hid[3]);
+          *reinterpret_cast<float2*>(dps + ra + 8 * nt + 2 * t) = make_float2(dpre[0], dpre[1]);
+          *reinterpret_cast<float2*>(dps + rb + 8 * nt + 2 * t) = make_float2(dpre[2], dpre[3]);
+        }
+      }
+      __syncwarp();
+      // ---- dx += dpre W1  (K = h) --------------------------------------------------------------
+#pragma unroll 1
+      for (int mt = 0; mt < 2; ++mt) {
+        const int ra = (r0 + 16 * mt + g) * XS, rb = ra + 8 * XS;
+        uint32_t ph[4][4], pl[4][4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          split_tf32(dps[ra + 8 * ks + t], ph[ks][0], pl[ks][0]);
+          split_tf32(dps[rb + 8 * ks + t], ph[ks][1], pl[ks][1]);
+          split_tf32(dps[ra + 8 * ks + t + 4], ph[ks][2], pl[ks][2]);
+          split_tf32(dps[rb + 8 * ks + t + 4], ph[ks][3], pl[ks][3]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {   // B[k = h][n = e] = W1[h][e]
+            uint32_t bh[2], bl[2];
+            split_tf32(w1[(8 * ks + t) * kWP + 8 * nt + g], bh[0], bl[0]);
+            split_tf32(w1[(8 * ks + t + 4) * kWP + 8 * nt + g], bh[1], bl[1]);
+            if (mt == 0) {
+              mma_tf32(dxa[0][nt], pl[ks], bh);
+              mma_tf32(dxa[0][nt], ph[ks], bl);
+              mma_tf32(dxa[0][nt], ph[ks], bh);
+            } else {
+              mma_tf32(dxa[1][nt], pl[ks], bh);
+              mma_tf32(dxa[1][nt], ph[ks], bl);
+              mma_tf32(dxa[1][nt], ph[ks], bh);
+            }
+          }
+        }
+      }
+
+      // ---- phase 2: dW1 += dpre^T x, dW2 += dout^T hid over this warp's rows (K = rows) ------------
+      float* acc_m = wsc + (long long)m * kAccBlk;
+      float d1[2][4][4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) d1[i][j][k] = 0.f;
+      float d2[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) d2[j][k] = 0.f;
+#pragma unroll 1
+      for (int ks = 0; ks < 4; ++ks) {
+        const int ra = (r0 + ks * 8 + t) * XS, rb = ra + 4 * XS;          // rows k = t and k = t + 4 of this step
+        uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {                                    // B = x[k][e]
+          split_tf32(xs[ra + nt * 8 + g], bh[nt][0], bl[nt][0]);
+          split_tf32(xs[rb + nt * 8 + g], bh[nt][1], bl[nt][1]);
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {                                    // A = dpre[k][h]^T
+          uint32_t ah[4], al[4];
+          split_tf32(dps[ra + mt * 16 + g], ah[0], al[0]);
+          split_tf32(dps[ra + mt * 16 + g + 8], ah[1], al[1]);
+          split_tf32(dps[rb + mt * 16 + g], ah[2], al[2]);
+          split_tf32(dps[rb + mt * 16 + g + 8], ah[3], al[3]);
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            mma_tf32(d1[mt][nt], al, bh[nt]);
+            mma_tf32(d1[mt][nt], ah, bl[nt]);
+            mma_tf32(d1[mt][nt], ah, bh[nt]);
+          }
+        }
+        const int da = (r0 + ks * 8 + t) * DS, db_ = da + 4 * DS;
+        uint32_t ah[4], al[4];                                              // A = dout[k][l]^T
+        split_tf32(dos[da + g], ah[0], al[0]);
+        split_tf32(dos[da + g + 8], ah[1], al[1]);
+        split_tf32(dos[db_ + g], ah[2], al[2]);
+        split_tf32(dos[db_ + g + 8], ah[3], al[3]);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {                                    // B = hid[k][h]
+          uint32_t hh[2], hl[2];
+          split_tf32(hs[ra + nt * 8 + g], hh[0], hl[0]);
+          split_tf32(hs[rb + nt * 8 + g], hh[1], hl[1]);
+          mma_tf32(d2[nt], al, hh);
+          mma_tf32(d2[nt], ah, hl);
+          mma_tf32(d2[nt], ah, hh);
+        }
+      }
+      {  // bias gradients: column sums over this warp's rows (lane = column)
+        float sb1 = 0.f, sb2 = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+          sb1 += dps[(r0 + r) * XS + lane];
+          sb2 += dos[(r0 + r) * DS + (lane & (GLP - 1))];
+        }
+        red_add1(acc_m + GH * GE + lane, sb1);
+        if (lane < GLP) red_add1(acc_m + GH * GE + GH + GLP * GH + lane, sb2);
+      }
+      // cross-warp sum of the partials through shared memory (dps / hs are dead once every warp is here)
+      constexpr int PS = 40;
+      float* part = dps;
+      static_assert(2 * kMT * XS >= (kMT / 32) * 48 * PS, "partial sums do not fit the dead tiles");
+      __syncthreads();
+      if (m + 1 < p.n_gen) request_weights(m + 1);   // nobody reads the weights any more
+      cp_async_commit();
+      float* mine = part + warp * 48 * PS;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          *reinterpret_cast<float2*>(mine + (mt * 16 + g) * PS + nt * 8 + 2 * t) = make_float2(d1[mt][nt][0], d1[mt][nt][1]);
+          *reinterpret_cast<float2*>(mine + (mt * 16 + g + 8) * PS + nt * 8 + 2 * t) = make_float2(d1[mt][nt][2], d1[mt][nt][3]);
+        }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        *reinterpret_cast<float2*>(mine + (32 + g) * PS + nt * 8 + 2 * t) = make_float2(d2[nt][0], d2[nt][1]);
+        *reinterpret_cast<float2*>(mine + (32 + g + 8) * PS + nt * 8 + 2 * t) = make_float2(d2[nt][2], d2[nt][3]);
+      }
+      __syncthreads();
+      for (int u = tid; u < 48 * 8; u += kMT) {
+        const int prow = u >> 3, col = (u & 7) * 4;
+        float4 sum = lds4g(part + prow * PS + col);
+#pragma unroll
+        for (int w = 1; w < kMT / 32; ++w) {
+          const float4 v = lds4g(part + (w * 48 + prow) * PS + col);
+          sum.x += v.x;
+          sum.y += v.y;
+          sum.z += v.z;
+          sum.w += v.w;
+        }
+        float* dst = prow < 32 ? acc_m + prow * GE + col : acc_m + GH * GE + GH + (prow - 32) * GH + col;
+        red_add4(dst, sum.x, sum.y, sum.z, sum.w);
+      }
+    }
+    // dx fragments -> global: rows r0 + 16 mt + g (+ 8), columns 8 nt + 2t, 2t + 1
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const long long ga = tile * kMT + r0 + 16 * mt + g, gb = ga + 8;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        if (ga < p.rows) *reinterpret_cast<float2*>(p.dx + ga * GE + 8 * nt + 2 * t) = make_float2(dxa[mt][nt][0], dxa[mt][nt][1]);
+        if (gb < p.rows) *reinterpret_cast<float2*>(p.dx + gb * GE + 8 * nt + 2 * t) = make_float2(dxa[mt][nt][2], dxa[mt][nt][3]);
+      }
+    }
+  }
+}
+
 // sum the per-CTA slices in a fixed order and scatter into the parameter-gradient tensors
 struct GenGrads {
   float *W1, *b1, *W2, *b2;     // stacked [n_W, ...]
@@ -743,6 +1044,7 @@ int gen_check(int64_t rows, int n_W, int E, int H, int L) {
   if (!g_gen_attr) {
     if (cudaFuncSetAttribute(psf_gen_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(psf_gen_bwd_kernel<kTB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBwd) != cudaSuccess ||
+        cudaFuncSetAttribute(psf_gen_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBwdMma) != cudaSuccess ||
         cudaFuncSetAttribute(psf_gen_bwd_kernel<kTB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBwd) != cudaSuccess) {
       cudaGetLastError();
       return PSF_ERR_UNSUPPORTED;
@@ -842,6 +1144,8 @@ int psf_generators_bwd(const psf_gen_desc* d, const float* x, psf_mlp_params fs,
   if (d->rows > 0) {
     if (pre_saved != nullptr)
       psf_gen_bwd_kernel<kTB, true><<<(unsigned)grid, kTB, kSmemBwd, st>>>(p);
+    else if (kBwdAllMma && kTB == kMT)
+      psf_gen_bwd_mma_kernel<<<(unsigned)grid, kMT, kSmemBwdMma, st>>>(p);
     else
       psf_gen_bwd_kernel<kTB, false><<<(unsigned)grid, kTB, kSmemBwd, st>>>(p);
     PSF_CUDA_TRY(cudaGetLastError());
