@@ -809,36 +809,55 @@ __global__ void __launch_bounds__(kMT, 3) psf_gen_bwd_mma_kernel(const GenParams
           split_tf32(dos[da + 8 * ks + t + 4], oh[ks][2], ol[ks][2]);
           split_tf32(dos[db_ + 8 * ks + t + 4], oh[ks][3], ol[ks][3]);
         }
+        // the four 8-column tiles are independent accumulators: their MMAs are interleaved so that the three
+        // dependent products of one tile are four instructions apart (the warp has few others to hide behind)
+        float pre[4][4], dh[4][4];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           const float bia0 = b1[8 * nt + 2 * t], bia1 = b1[8 * nt + 2 * t + 1];
-          float pre[4] = {bia0, bia1, bia0, bia1};
+          pre[nt][0] = pre[nt][2] = bia0;
+          pre[nt][1] = pre[nt][3] = bia1;
+          dh[nt][0] = dh[nt][1] = dh[nt][2] = dh[nt][3] = 0.f;
+        }
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {   // B[k = e][n = h] = W1[h][e]
-            uint32_t bh[2], bl[2];
-            split_tf32(w1[(8 * nt + g) * kWP + 8 * ks + t], bh[0], bl[0]);
-            split_tf32(w1[(8 * nt + g) * kWP + 8 * ks + t + 4], bh[1], bl[1]);
-            mma_tf32(pre, xl[ks], bh);
-            mma_tf32(pre, xh[ks], bl);
-            mma_tf32(pre, xh[ks], bh);
-          }
-          float dh[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int ks = 0; ks < 4; ++ks) {   // B[k = e][n = h] = W1[h][e]
+          uint32_t bh[4][2], bl[4][2];
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {   // B[k = l][n = h] = W2[l][h]
-            uint32_t bh[2], bl[2];
-            split_tf32(w2[(8 * ks + t) * kWP + 8 * nt + g], bh[0], bl[0]);
-            split_tf32(w2[(8 * ks + t + 4) * kWP + 8 * nt + g], bh[1], bl[1]);
-            mma_tf32(dh, ol[ks], bh);
-            mma_tf32(dh, oh[ks], bl);
-            mma_tf32(dh, oh[ks], bh);
+          for (int nt = 0; nt < 4; ++nt) {
+            split_tf32(w1[(8 * nt + g) * kWP + 8 * ks + t], bh[nt][0], bl[nt][0]);
+            split_tf32(w1[(8 * nt + g) * kWP + 8 * ks + t + 4], bh[nt][1], bl[nt][1]);
           }
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) mma_tf32(pre[nt], xl[ks], bh[nt]);
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) mma_tf32(pre[nt], xh[ks], bl[nt]);
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) mma_tf32(pre[nt], xh[ks], bh[nt]);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {   // B[k = l][n = h] = W2[l][h]
+          uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            split_tf32(w2[(8 * ks + t) * kWP + 8 * nt + g], bh[nt][0], bl[nt][0]);
+            split_tf32(w2[(8 * ks + t + 4) * kWP + 8 * nt + g], bh[nt][1], bl[nt][1]);
+          }
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) mma_tf32(dh[nt], ol[ks], bh[nt]);
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) mma_tf32(dh[nt], oh[ks], bl[nt]);
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) mma_tf32(dh[nt], oh[ks], bh[nt]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
           float hid[4], dpre[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             float cdf, pdf;
-            normal_cdf_pdf_fast(pre[i], cdf, pdf);
-            hid[i] = pre[i] * cdf;
-            dpre[i] = dh[i] * (cdf + pre[i] * pdf);
+            normal_cdf_pdf_fast(pre[nt][i], cdf, pdf);
+            hid[i] = pre[nt][i] * cdf;
+            dpre[i] = dh[nt][i] * (cdf + pre[nt][i] * pdf);
           }
           // fragment (c0, c1) = row g, columns 2t, 2t+1 of the 8-column tile; (c2, c3) = row g + 8
           *reinterpret_cast<float2*>(hs + ra + 8 * nt + 2 * t) = make_float2(hid[0], hid[1]);
@@ -861,21 +880,27 @@ __global__ void __launch_bounds__(kMT, 3) psf_gen_bwd_mma_kernel(const GenParams
           split_tf32(dps[rb + 8 * ks + t + 4], ph[ks][3], pl[ks][3]);
         }
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
+        for (int ks = 0; ks < 4; ++ks) {   // B[k = h][n = e] = W1[h][e]
+          uint32_t bh[4][2], bl[4][2];
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {   // B[k = h][n = e] = W1[h][e]
-            uint32_t bh[2], bl[2];
-            split_tf32(w1[(8 * ks + t) * kWP + 8 * nt + g], bh[0], bl[0]);
-            split_tf32(w1[(8 * ks + t + 4) * kWP + 8 * nt + g], bh[1], bl[1]);
-            if (mt == 0) {
-              mma_tf32(dxa[0][nt], pl[ks], bh);
-              mma_tf32(dxa[0][nt], ph[ks], bl);
-              mma_tf32(dxa[0][nt], ph[ks], bh);
-            } else {
-              mma_tf32(dxa[1][nt], pl[ks], bh);
-              mma_tf32(dxa[1][nt], ph[ks], bl);
-              mma_tf32(dxa[1][nt], ph[ks], bh);
-            }
+          for (int nt = 0; nt < 4; ++nt) {
+            split_tf32(w1[(8 * ks + t) * kWP + 8 * nt + g], bh[nt][0], bl[nt][0]);
+            split_tf32(w1[(8 * ks + t + 4) * kWP + 8 * nt + g], bh[nt][1], bl[nt][1]);
+          }
+          if (mt == 0) {
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) mma_tf32(dxa[0][nt], pl[ks], bh[nt]);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) mma_tf32(dxa[0][nt], ph[ks], bl[nt]);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) mma_tf32(dxa[0][nt], ph[ks], bh[nt]);
+          } else {
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) mma_tf32(dxa[1][nt], pl[ks], bh[nt]);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) mma_tf32(dxa[1][nt], ph[ks], bl[nt]);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) mma_tf32(dxa[1][nt], ph[ks], bh[nt]);
           }
         }
       }
@@ -911,11 +936,11 @@ __global__ void __launch_bounds__(kMT, 3) psf_gen_bwd_mma_kernel(const GenParams
           split_tf32(dps[rb + mt * 16 + g], ah[2], al[2]);
           split_tf32(dps[rb + mt * 16 + g + 8], ah[3], al[3]);
 #pragma unroll
-          for (int nt = 0; nt < 4; ++nt) {
-            mma_tf32(d1[mt][nt], al, bh[nt]);
-            mma_tf32(d1[mt][nt], ah, bl[nt]);
-            mma_tf32(d1[mt][nt], ah, bh[nt]);
-          }
+          for (int nt = 0; nt < 4; ++nt) mma_tf32(d1[mt][nt], al, bh[nt]);
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) mma_tf32(d1[mt][nt], ah, bl[nt]);
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) mma_tf32(d1[mt][nt], ah, bh[nt]);
         }
         const int da = (r0 + ks * 8 + t) * DS, db_ = da + 4 * DS;
         uint32_t ah[4], al[4];                                              // A = dout[k][l]^T
@@ -923,15 +948,18 @@ __global__ void __launch_bounds__(kMT, 3) psf_gen_bwd_mma_kernel(const GenParams
         split_tf32(dos[da + g + 8], ah[1], al[1]);
         split_tf32(dos[db_ + g], ah[2], al[2]);
         split_tf32(dos[db_ + g + 8], ah[3], al[3]);
+        uint32_t hh[4][2], hl[4][2];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {                                    // B = hid[k][h]
-          uint32_t hh[2], hl[2];
-          split_tf32(hs[ra + nt * 8 + g], hh[0], hl[0]);
-          split_tf32(hs[rb + nt * 8 + g], hh[1], hl[1]);
-          mma_tf32(d2[nt], al, hh);
-          mma_tf32(d2[nt], ah, hl);
-          mma_tf32(d2[nt], ah, hh);
+          split_tf32(hs[ra + nt * 8 + g], hh[nt][0], hl[nt][0]);
+          split_tf32(hs[rb + nt * 8 + g], hh[nt][1], hl[nt][1]);
         }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_tf32(d2[nt], al, hh[nt]);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_tf32(d2[nt], ah, hl[nt]);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_tf32(d2[nt], ah, hh[nt]);
       }
       {  // bias gradients: column sums over this warp's rows (lane = column)
         float sb1 = 0.f, sb2 = 0.f;
