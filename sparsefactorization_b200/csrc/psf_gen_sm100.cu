@@ -20,13 +20,11 @@
 //                        groups with a shuffle reduce-scatter, accumulated into a per-CTA slice of a
 //                        global workspace (fire-and-forget red.add by the one owning thread: deterministic).
 //             A second tiny kernel sums the per-CTA slices in a fixed order.
-#include "psf_internal.cuh"
+#include <stdlib.h>
+#include "psf_gen.cuh"
 
 namespace {
 
-constexpr int GE = 32;    // embedding width
-constexpr int GH = 32;    // hidden width
-constexpr int GLP = 16;   // taps padded
 constexpr int kBlkFwd = GH * GE + GH + GH * GLP + GLP;  // w1[h][e], b1[h], w2t[h][l], b2[l]  = 1584 floats
 constexpr int kBlkBwd = GH * GE + GH + GLP * GH;        // w1[h][e], b1[h], w2[l][h]          = 1568 floats
 constexpr int kAccBlk = GH * GE + GH + GLP * GH + GLP;  // dW1, db1, dW2 (l-major, padded), db2 = 1584 floats
@@ -103,55 +101,6 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-struct GenParams {
-  const float* x;
-  const float* W1;  // [n_W][32][32]
-  const float* b1;  // [n_W][32]
-  const float* W2;  // [n_W][L][32]
-  const float* b2;  // [n_W][L]
-  const float* gW1; // optional V generator g (psf.py:126): [32][32], [32], [C][32], [C]; generator index n_W
-  const float* gb1;
-  const float* gW2;
-  const float* gb2;
-  float* Wt;        // fwd: out [n_W][L][rows];  bwd: dW (same layout, read)
-  float* V;         // fwd: V0 [rows][C] in NATURAL row order;  bwd: dV0 (read)
-  float* dx;        // bwd: [rows][32]
-  float* ws;        // bwd: [grid][n_gen][kAccBlk]
-  float* pre;       // optional [n_gen][32][rows]: pre-activations saved by the forward pass for the backward pass
-  long long rows, sWf, sWt;
-  int n_W, L;
-  int n_gen;        // n_W + (g present)
-  int C;            // outputs of g
-  int n, Q;         // rows per sample and row interleave of x (to find the natural row of a V0 row)
-};
-
-// generator m's parameter tensors and output count
-__device__ __forceinline__ void gen_ptrs(const GenParams& p, int m, const float*& W1, const float*& b1, const float*& W2,
-                                         const float*& b2, int& Lm) {
-  if (m < p.n_W) {
-    W1 = p.W1 + (long long)m * GH * GE;
-    b1 = p.b1 + m * GH;
-    W2 = p.W2 + (long long)m * p.L * GH;
-    b2 = p.b2 + m * p.L;
-    Lm = p.L;
-  } else {
-    W1 = p.gW1;
-    b1 = p.gb1;
-    W2 = p.gW2;
-    b2 = p.gb2;
-    Lm = p.C;
-  }
-}
-// natural row index of row `row` of a quad-interleaved x (include/psf_b200.h)
-__device__ __forceinline__ long long natural_row(const GenParams& p, long long row) {
-  if (p.Q <= 1) return row;
-  const long long b = row / p.n;
-  const int pos = (int)(row - b * p.n);
-  const int J = p.n / p.Q;
-  const int q = pos / J, r = pos - q * J;
-  return b * p.n + 4 * ((r >> 2) * p.Q + q) + (r & 3);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1054,6 +1003,15 @@ __global__ void psf_gen_reduce_kernel(const float* __restrict__ ws, int nslices,
 
 bool g_gen_attr = false;
 
+// PSF_GEN_TC=0 in the environment keeps the FP32-FMA / mma.sync kernels (A/B timing, parity cross-checks)
+bool gen_use_tc() {
+  static const bool on = [] {
+    const char* e = getenv("PSF_GEN_TC");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
+}
+
 int gen_grid(int per_sm) {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1133,6 +1091,10 @@ int psf_generators_fwd(const psf_gen_desc* d, const float* x, psf_mlp_params fs,
   p.Wt = W_out;
   p.V = V_out;
   p.pre = pre_save;
+  if (gen_use_tc() && pre_save == nullptr) {   // tcgen05 / tensor-memory kernel (psf_gen_tc_sm100.cu)
+    rc = psf_gen_tc_fwd(p, (cudaStream_t)stream);
+    if (rc != PSF_ERR_UNSUPPORTED) return rc;
+  }
   const long long ntiles = (d->rows + 2 * kFT - 1) / (2 * kFT);
   long long grid = gen_grid(2);
   if (grid > ntiles) grid = ntiles;
