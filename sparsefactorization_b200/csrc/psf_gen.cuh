@@ -6,6 +6,7 @@
 constexpr int GE = 32;    // embedding width
 constexpr int GH = 32;    // hidden width
 constexpr int GLP = 16;   // taps padded
+constexpr int kAccBlk = GH * GE + GH + GLP * GH + GLP;  // parameter-gradient block of one generator: dW1, db1, dW2 (l-major, padded), db2
 
 struct GenParams {
   const float* x;
@@ -59,3 +60,7 @@ static __device__ __forceinline__ long long natural_row(const GenParams& p, long
 // tcgen05 kernels (psf_gen_tc_sm100.cu).  Return PSF_ERR_UNSUPPORTED when the shape is not covered (the caller then
 // launches the FP32-FMA kernel), else the launch status.
 int psf_gen_tc_fwd(const GenParams& p, cudaStream_t st);
+// backward: `images` = psf_gen_tc_bwd_image_bytes(n_gen) bytes of 128-byte aligned device scratch (overwritten); p.ws =
+// zeroed [*grid_out][n_gen][kAccBlk] accumulator slices (the caller reduces them)
+size_t psf_gen_tc_bwd_image_bytes(int n_gen);
+int psf_gen_tc_bwd(const GenParams& p, void* images, int* grid_out, cudaStream_t st);

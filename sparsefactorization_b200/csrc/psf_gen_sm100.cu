@@ -27,7 +27,6 @@ namespace {
 
 constexpr int kBlkFwd = GH * GE + GH + GH * GLP + GLP;  // w1[h][e], b1[h], w2t[h][l], b2[l]  = 1584 floats
 constexpr int kBlkBwd = GH * GE + GH + GLP * GH;        // w1[h][e], b1[h], w2[l][h]          = 1568 floats
-constexpr int kAccBlk = GH * GE + GH + GLP * GH + GLP;  // dW1, db1, dW2 (l-major, padded), db2 = 1584 floats
 // phase 2 of the backward kernel (parameter-gradient GEMMs): 1 = tensor cores (mma.sync 3xTF32), 0 = FP32 FMA tiles
 #ifndef PSF_GEN_MMA
 #define PSF_GEN_MMA 1
@@ -1044,9 +1043,13 @@ int gen_check(int64_t rows, int n_W, int E, int H, int L) {
 
 extern "C" {
 
+static size_t gen_slices_bytes(int n_W) {
+  return psf_round256((size_t)gen_grid(384 / kTB) * (size_t)(n_W + 1) * kAccBlk * sizeof(float));
+}
 size_t psf_generators_workspace_bytes(int n_W) {
   if (n_W < 1) return 0;
-  return psf_round256((size_t)gen_grid(384 / kTB) * (size_t)(n_W + 1) * kAccBlk * sizeof(float));
+  // per-CTA parameter-gradient slices, then the weight images of the tcgen05 kernel
+  return gen_slices_bytes(n_W) + psf_round256(psf_gen_tc_bwd_image_bytes(n_W + 1));
 }
 
 static int gen_fill(GenParams& p, const psf_gen_desc* d, const float* x, const psf_mlp_params& fs, const psf_mlp_params& g) {
@@ -1131,6 +1134,17 @@ int psf_generators_bwd(const psf_gen_desc* d, const float* x, psf_mlp_params fs,
   p.dx = dx;
   p.ws = (float*)workspace;
   p.pre = const_cast<float*>(pre_saved);
+  if (d->rows > 0 && pre_saved == nullptr && gen_use_tc()) {   // tcgen05 / tensor-memory kernel (psf_gen_tc_bwd_sm100.cu)
+    int tc_grid = 0;
+    rc = psf_gen_tc_bwd(p, (char*)workspace + gen_slices_bytes(d->n_W), &tc_grid, st);
+    if (rc != PSF_ERR_UNSUPPORTED) {
+      if (rc) return rc;
+      GenGrads gg = {dfs.W1, dfs.b1, dfs.W2, dfs.b2, dg.W1, dg.b1, dg.W2, dg.b2};
+      psf_gen_reduce_kernel<<<(p.n_gen * kAccBlk + 255) / 256, 256, 0, st>>>((const float*)workspace, tc_grid, p.n_W, p.n_gen,
+                                                                             p.L, p.C, gg);
+      return (int)cudaGetLastError();
+    }
+  }
   if (d->rows > 0) {
     if (pre_saved != nullptr)
       psf_gen_bwd_kernel<kTB, true><<<(unsigned)grid, kTB, kSmemBwd, st>>>(p);

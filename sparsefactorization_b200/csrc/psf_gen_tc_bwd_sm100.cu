@@ -1,0 +1,533 @@
+// Backward pass of the generators on tcgen05 + tensor memory (sm_100a); forward: psf_gen_tc_sm100.cu.
+//
+// For a 128-row tile and generator m = Linear(32,32) -> GELU -> Linear(32,L) (SyntheticExperiments/psf.py:110-126):
+//
+//   tcgen05 (A operand in TENSOR MEMORY, lane = row; B = weights in shared memory, K-major, staged per generator by TMA)
+//     pre  [128 x 32] = x    [128 x 32] . W1^T        (recomputed: saving it would be 4 GB)
+//     dhid [128 x 32] = dout [128 x 16] . W2
+//     dx   [128 x 32] += dpre[128 x 32] . W1          (one accumulator over all generators of the tile)
+//   epilogue warps (thread = row): tcgen05.ld of pre / dhid, Phi / phi, hid = pre Phi, dpre = dhid (Phi + pre phi);
+//     dpre goes back to tensor memory as the A operand of the dx product
+//   warp-level mma.sync (K = rows, so the operands would have to be transposed for tcgen05 - the staged shared-memory
+//     tiles are read as fragments instead): dW1 += dpre^T x, dW2 += dout^T hid over the warp's own 32 rows; the four
+//     warps' partial results are summed through shared memory and added to the CTA's slice of a global workspace
+//
+// Every product is error-compensated 3xTF32 (psf_gen_tc_sm100.cu); small terms first.
+//
+// Warp roles (448 threads, one CTA per SM, persistent):
+//   warps 0-7   two epilogue warpgroups; consecutive generators alternate between them
+//   warps 8-11  x loader (tensor memory + shared memory) and dx writer
+//   warp 12     tensor-memory allocation + the MMA-issuing thread
+//   warp 13     one thread streaming the per-generator weight images (TMA bulk copies, 4-stage ring)
+#include "psf_gen.cuh"
+#include "psf_tc.cuh"
+
+namespace {
+
+constexpr int kThreadsBwd = 14 * 32;
+constexpr int kWarpLoad0 = 8, kWarpMma = 12, kWarpTma = 13;
+constexpr int XS = GE + 4;    // padded row of the staged fp32 tiles (conflict-free fragment loads)
+constexpr int DS = GLP + 4;
+constexpr int X2S = 72;       // row of the (hi, lo)-interleaved x tile, in floats
+// weight image of one generator (bytes): W1 [n=h][k=e] hi, lo | W1^T [n=e][k=h] hi, lo | W2^T [n=h][k=l] hi, lo
+constexpr uint32_t kImgW1 = 0, kImgW1T = 8192, kImgW2T = 16384, kImgBytes = 20480;
+constexpr int kStages = 4;
+// shared memory
+constexpr uint32_t kOffXs = kStages * kImgBytes;                     // [128][X2S] floats
+constexpr uint32_t kOffStage = kOffXs + 128 * X2S * 4;               // per warpgroup: dps, hs, dos
+constexpr uint32_t kStageBytes = (2 * 128 * XS + 128 * DS) * 4;
+constexpr uint32_t kOffBarB = kOffStage + 2 * kStageBytes;
+constexpr uint32_t kSmemBwdTC = kOffBarB + 256;
+// tensor-memory columns
+constexpr uint32_t kTX = 0, kTXlo = 32, kTDx = 64, kTWg = 96, kTWgStride = 160;
+constexpr uint32_t kTPre = 0, kTDhid = 32, kTDout = 64, kTDoutLo = 80, kTDpre = 96, kTDpreLo = 128;
+
+enum {
+  B_XFULL = 0, B_XEMPTY, B_XSFULL, B_XSFREE, B_DXFULL, B_DXEMPTY,
+  B_WFULL0, B_WEMPTY0 = B_WFULL0 + kStages,
+  B_DOUTFULL0 = B_WEMPTY0 + kStages, B_PDFULL0 = B_DOUTFULL0 + 2, B_DPREFULL0 = B_PDFULL0 + 2, B_DPREFREE0 = B_DPREFULL0 + 2,
+  B_COUNT = B_DPREFREE0 + 2
+};
+static_assert(B_COUNT * 8 + 8 <= 256, "barrier block");
+
+__device__ __forceinline__ void red_add4g(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add1g(float* p, float a) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
+}
+// truncating split for the mma.sync operands (the tensor core ignores the low 13 bits of hi and of lo)
+__device__ __forceinline__ void split_trunc(float v, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(v) & 0xffffe000u;
+  lo = __float_as_uint(v - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32_sync(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void wg_bar(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory"); }
+
+// Phi(p) and phi(p) from one exp(-p^2/2): erfc by the 6-term A&S-type fit of psf_gen_tc_sm100.cu (|error| < 1e-7 in fp32)
+__device__ __forceinline__ void normal_cdf_pdf(float p, float& cdf, float& pdf) {
+  const float ax = fabsf(p);
+  const float t = rcp_approx(fmaf(ax, 0.27599917f, 1.f));
+  float q = fmaf(-0.22690525f, t, 0.88164259f);
+  q = fmaf(q, t, -0.62774200f);
+  q = fmaf(q, t, 0.64431879f);
+  q = fmaf(q, t, 0.093436931f);
+  q = fmaf(q, t, 0.23524893f);
+  const float e = ex2_approx(p * p * -0.72134752f);
+  const float tail = 0.5f * (q * t) * e;          // Phi(-|p|)
+  cdf = p >= 0.f ? 1.f - tail : tail;
+  pdf = 0.39894228f * e;
+}
+
+// weights -> MMA-ready images (3xTF32 hi / lo, K-major core-matrix layout), once per backward call
+__global__ void psf_gen_tc_prep_kernel(const GenParams p, uint8_t* __restrict__ img) {
+  const int m = blockIdx.x;
+  const float* W1 = m < p.n_W ? p.W1 + (long long)m * GH * GE : p.gW1;
+  const float* W2 = m < p.n_W ? p.W2 + (long long)m * p.L * GH : p.gW2;
+  const int Lm = m < p.n_W ? p.L : p.C;
+  uint8_t* dst = img + (size_t)m * kImgBytes;
+  for (int idx = threadIdx.x; idx < GH * GE; idx += blockDim.x) {
+    const int h = idx >> 5, e = idx & 31;
+    const float v = W1[idx];
+    const uint32_t o1 = kImgW1 + (h >> 3) * 1024 + (e >> 2) * 128 + (h & 7) * 16 + (e & 3) * 4;
+    const uint32_t o2 = kImgW1T + (e >> 3) * 1024 + (h >> 2) * 128 + (e & 7) * 16 + (h & 3) * 4;
+    *reinterpret_cast<float*>(dst + o1) = tf32_hi(v);
+    *reinterpret_cast<float*>(dst + o1 + 4096) = tf32_lo(v);
+    *reinterpret_cast<float*>(dst + o2) = tf32_hi(v);
+    *reinterpret_cast<float*>(dst + o2 + 4096) = tf32_lo(v);
+  }
+  for (int idx = threadIdx.x; idx < GLP * GH; idx += blockDim.x) {
+    const int l = idx >> 5, h = idx & 31;
+    const float v = l < Lm ? W2[l * GH + h] : 0.f;
+    const uint32_t o = kImgW2T + (h >> 3) * 512 + (l >> 2) * 128 + (h & 7) * 16 + (l & 3) * 4;
+    *reinterpret_cast<float*>(dst + o) = tf32_hi(v);
+    *reinterpret_cast<float*>(dst + o + 2048) = tf32_lo(v);
+  }
+}
+
+__global__ void __launch_bounds__(kThreadsBwd, 1) psf_gen_bwd_tc_kernel(const GenParams p, const uint8_t* __restrict__ img) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bars = sbase + kOffBarB;
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + kOffBarB + B_COUNT * 8);
+  const int n_gen = p.n_gen;
+  float* xs2 = reinterpret_cast<float*>(smem + kOffXs);
+
+  if (tid == 0) {
+    mbar_init(bars + 8 * B_XFULL, 4);
+    mbar_init(bars + 8 * B_XEMPTY, 1);
+    mbar_init(bars + 8 * B_XSFULL, 4);
+    mbar_init(bars + 8 * B_XSFREE, 8);
+    mbar_init(bars + 8 * B_DXFULL, 1);
+    mbar_init(bars + 8 * B_DXEMPTY, 4);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(bars + 8 * (B_WFULL0 + i), 1);
+      mbar_init(bars + 8 * (B_WEMPTY0 + i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bars + 8 * (B_DOUTFULL0 + i), 4);
+      mbar_init(bars + 8 * (B_PDFULL0 + i), 1);
+      mbar_init(bars + 8 * (B_DPREFULL0 + i), 4);
+      mbar_init(bars + 8 * (B_DPREFREE0 + i), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kWarpMma) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tslot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+
+  const long long ntiles = (p.rows + 127) >> 7;
+  const int my_tiles = (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  const uint32_t total = (uint32_t)my_tiles * (uint32_t)n_gen;     // (tile, generator) steps of this CTA, in order
+  float* wsc = p.ws + (long long)blockIdx.x * n_gen * kAccBlk;
+
+  if (warp < kWarpLoad0) {
+    // ======================================= epilogue warpgroups =======================================
+    const int wg = warp >> 2, quarter = warp & 3;
+    const int g = lane >> 2, t = lane & 3;
+    const int r0 = quarter * 32, rl = r0 + lane;
+    const uint32_t lane_base = ((uint32_t)quarter * 32u) << 16;
+    const uint32_t twg = tmem + lane_base + kTWg + kTWgStride * wg;
+    float* dps = reinterpret_cast<float*>(smem + kOffStage + wg * kStageBytes);
+    float* hs = dps + 128 * XS;
+    float* dos = hs + 128 * XS;
+    const uint32_t bar_dout = bars + 8 * (B_DOUTFULL0 + wg), bar_pd = bars + 8 * (B_PDFULL0 + wg);
+    const uint32_t bar_dpre = bars + 8 * (B_DPREFULL0 + wg), bar_free = bars + 8 * (B_DPREFREE0 + wg);
+
+    auto row_of = [&](uint32_t s) { return (blockIdx.x + (long long)(s / (uint32_t)n_gen) * gridDim.x) * 128 + rl; };
+    auto load_dout = [&](uint32_t s, float (&d)[GLP]) {
+      const int m = (int)(s % (uint32_t)n_gen);
+      const long long row = row_of(s);
+      const bool live = row < p.rows;
+      if (m < p.n_W) {
+        const float* src = p.Wt + (long long)m * p.sWf + row;
+#pragma unroll
+        for (int l = 0; l < GLP; ++l) d[l] = (live && l < p.L) ? __ldcs(src + (long long)l * p.sWt) : 0.f;
+      } else {
+        const float* src = p.V + (live ? natural_row(p, row) : 0) * p.C;
+#pragma unroll
+        for (int c = 0; c < GLP; ++c) d[c] = (live && c < p.C) ? __ldcs(src + c) : 0.f;
+      }
+    };
+    // dout -> tensor memory (A operand of dhid = dout W2), hi then lo
+    auto publish_dout = [&](const float (&d)[GLP]) {
+      float hi[GLP], lo[GLP];
+#pragma unroll
+      for (int l = 0; l < GLP; ++l) {
+        hi[l] = tf32_hi(d[l]);
+        lo[l] = d[l] - hi[l];
+      }
+      tmem_st16f(twg + kTDout, hi);
+      tmem_st16f(twg + kTDoutLo, lo);
+      tmem_wait_st_tc();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_dout);
+    };
+    auto stage_dout = [&](const float (&d)[GLP]) {
+#pragma unroll
+      for (int i = 0; i < GLP / 4; ++i)
+        *reinterpret_cast<float4*>(dos + rl * DS + 4 * i) = make_float4(d[4 * i], d[4 * i + 1], d[4 * i + 2], d[4 * i + 3]);
+    };
+
+    float dn[GLP];
+    uint32_t k = 0;
+    if ((uint32_t)wg < total) {
+      load_dout((uint32_t)wg, dn);
+      publish_dout(dn);
+      stage_dout(dn);
+    }
+    for (uint32_t s = (uint32_t)wg; s < total; s += 2, ++k) {
+      const int m = (int)(s % (uint32_t)n_gen);
+      const uint32_t it = s / (uint32_t)n_gen;
+      const bool has_next = s + 2 < total;
+      if (has_next) load_dout(s + 2, dn);                 // streamed from HBM a generator ahead
+      const float* b1 = m < p.n_W ? p.b1 + m * GH : p.gb1;
+      float pre[GH], dh[GH];
+      mbar_wait_tc(bar_pd, k & 1);
+      tc_fence_after();
+      tmem_ld32f(twg + kTPre, pre);
+      tmem_ld32f(twg + kTDhid, dh);
+      tmem_wait_ld_tc();
+      if (has_next) publish_dout(dn);                     // pre / dhid of the next generator are computed meanwhile
+#pragma unroll
+      for (int h4 = 0; h4 < GH / 4; ++h4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(b1) + h4);
+        const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int h = 4 * h4 + j;
+          const float pv = pre[h] + bb[j];
+          float cdf, pdf;
+          normal_cdf_pdf(pv, cdf, pdf);
+          pre[h] = dh[h] * fmaf(pv, pdf, cdf);            // dpre
+          dh[h] = pv * cdf;                               // hid
+        }
+      }
+      // stage for the parameter-gradient products (this warp's rows)
+#pragma unroll
+      for (int i = 0; i < GH / 4; ++i) {
+        *reinterpret_cast<float4*>(dps + rl * XS + 4 * i) = make_float4(pre[4 * i], pre[4 * i + 1], pre[4 * i + 2], pre[4 * i + 3]);
+        *reinterpret_cast<float4*>(hs + rl * XS + 4 * i) = make_float4(dh[4 * i], dh[4 * i + 1], dh[4 * i + 2], dh[4 * i + 3]);
+      }
+      // dpre -> tensor memory (A operand of dx += dpre W1)
+      mbar_wait_tc(bar_free, (k & 1) ^ 1);
+      tc_fence_after();
+      {
+#pragma unroll
+        for (int h = 0; h < GH; ++h) dh[h] = tf32_hi(pre[h]);
+        tmem_st32f(twg + kTDpre, dh);
+#pragma unroll
+        for (int h = 0; h < GH; ++h) pre[h] -= dh[h];
+        tmem_st32f(twg + kTDpreLo, pre);
+        tmem_wait_st_tc();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_dpre);
+      }
+      mbar_wait_tc(bars + 8 * B_XSFULL, it & 1);          // x of this tile is in shared memory
+      __syncwarp();
+
+      // ---- dW1[h][e] += dpre^T x, dW2[l][h] += dout^T hid over this warp's 32 rows (mma.sync m16n8k8, 3xTF32) ----
+      float* acc_m = wsc + (long long)m * kAccBlk;
+      float d1[2][4][4], d2[4][4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) d1[i][j][q] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) d2[j][q] = 0.f;
+#pragma unroll 1
+      for (int ks = 0; ks < 4; ++ks) {
+        const int ra = r0 + ks * 8 + t, rb = ra + 4;               // rows k = t and k = t + 4 of this step
+        uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {                           // B = x[k][e], pre-split
+          const float2 va = *reinterpret_cast<const float2*>(xs2 + ra * X2S + 2 * (nt * 8 + g));
+          const float2 vb = *reinterpret_cast<const float2*>(xs2 + rb * X2S + 2 * (nt * 8 + g));
+          bh[nt][0] = __float_as_uint(va.x);
+          bl[nt][0] = __float_as_uint(va.y);
+          bh[nt][1] = __float_as_uint(vb.x);
+          bl[nt][1] = __float_as_uint(vb.y);
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {                           // A = dpre[k][h]^T
+          uint32_t ah[4], al[4];
+          split_trunc(dps[ra * XS + mt * 16 + g], ah[0], al[0]);
+          split_trunc(dps[ra * XS + mt * 16 + g + 8], ah[1], al[1]);
+          split_trunc(dps[rb * XS + mt * 16 + g], ah[2], al[2]);
+          split_trunc(dps[rb * XS + mt * 16 + g + 8], ah[3], al[3]);
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) mma_tf32_sync(d1[mt][nt], al, bh[nt]);
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) mma_tf32_sync(d1[mt][nt], ah, bl[nt]);
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) mma_tf32_sync(d1[mt][nt], ah, bh[nt]);
+        }
+        uint32_t ah[4], al[4];                                     // A = dout[k][l]^T
+        split_trunc(dos[ra * DS + g], ah[0], al[0]);
+        split_trunc(dos[ra * DS + g + 8], ah[1], al[1]);
+        split_trunc(dos[rb * DS + g], ah[2], al[2]);
+        split_trunc(dos[rb * DS + g + 8], ah[3], al[3]);
+        uint32_t hh[4][2], hl[4][2];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {                           // B = hid[k][h]
+          split_trunc(hs[ra * XS + nt * 8 + g], hh[nt][0], hl[nt][0]);
+          split_trunc(hs[rb * XS + nt * 8 + g], hh[nt][1], hl[nt][1]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_tf32_sync(d2[nt], al, hh[nt]);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_tf32_sync(d2[nt], ah, hl[nt]);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_tf32_sync(d2[nt], ah, hh[nt]);
+      }
+      {  // bias gradients: column sums over this warp's rows (lane = column)
+        float sb1 = 0.f, sb2 = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+          sb1 += dps[(r0 + r) * XS + lane];
+          sb2 += dos[(r0 + r) * DS + (lane & (GLP - 1))];
+        }
+        red_add1g(acc_m + GH * GE + lane, sb1);
+        if (lane < GLP) red_add1g(acc_m + GH * GE + GH + GLP * GH + lane, sb2);
+      }
+      // cross-warp sum through shared memory (the dpre / hid tiles are dead once all four warps are here)
+      constexpr int PS = 40;
+      static_assert(2 * 128 * XS >= 4 * 48 * PS, "partial sums do not fit the dead tiles");
+      float* part = dps;
+      wg_bar(wg);
+      float* mine = part + quarter * 48 * PS;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          *reinterpret_cast<float2*>(mine + (mt * 16 + g) * PS + nt * 8 + 2 * t) = make_float2(d1[mt][nt][0], d1[mt][nt][1]);
+          *reinterpret_cast<float2*>(mine + (mt * 16 + g + 8) * PS + nt * 8 + 2 * t) = make_float2(d1[mt][nt][2], d1[mt][nt][3]);
+        }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        *reinterpret_cast<float2*>(mine + (32 + g) * PS + nt * 8 + 2 * t) = make_float2(d2[nt][0], d2[nt][1]);
+        *reinterpret_cast<float2*>(mine + (32 + g + 8) * PS + nt * 8 + 2 * t) = make_float2(d2[nt][2], d2[nt][3]);
+      }
+      wg_bar(wg);
+      for (int u = quarter * 32 + lane; u < 48 * 8; u += 128) {
+        const int prow = u >> 3, col = (u & 7) * 4;
+        float4 sum = *reinterpret_cast<const float4*>(part + prow * PS + col);
+#pragma unroll
+        for (int w = 1; w < 4; ++w) {
+          const float4 v = *reinterpret_cast<const float4*>(part + (w * 48 + prow) * PS + col);
+          sum.x += v.x;
+          sum.y += v.y;
+          sum.z += v.z;
+          sum.w += v.w;
+        }
+        float* dst = prow < 32 ? acc_m + prow * GE + col : acc_m + GH * GE + GH + (prow - 32) * GH + col;
+        red_add4g(dst, sum.x, sum.y, sum.z, sum.w);
+      }
+      wg_bar(wg);
+      if (!has_next || (s + 2) / (uint32_t)n_gen != it) {   // this warpgroup is done with the tile's x
+        if (lane == 0) mbar_arrive(bars + 8 * B_XSFREE);
+      }
+      if (has_next) stage_dout(dn);
+    }
+  } else if (warp < kWarpMma) {
+    // ======================================= x loader / dx writer =======================================
+    const int quarter = warp & 3;
+    const int rl = quarter * 32 + lane;
+    const uint32_t lane_base = ((uint32_t)quarter * 32u) << 16;
+    auto write_dx = [&](int it) {
+      const long long row = (blockIdx.x + (long long)it * gridDim.x) * 128 + rl;
+      float v[GE];
+      mbar_wait_relaxed(bars + 8 * B_DXFULL, it & 1);
+      tc_fence_after();
+      tmem_ld32f(tmem + lane_base + kTDx, v);
+      tmem_wait_ld_tc();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 8 * B_DXEMPTY);
+      if (row < p.rows) {
+        float4* dst = reinterpret_cast<float4*>(p.dx + row * GE);
+#pragma unroll
+        for (int i = 0; i < GE / 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+    };
+    for (int it = 0; it < my_tiles; ++it) {
+      const long long row = (blockIdx.x + (long long)it * gridDim.x) * 128 + rl;
+      float v[GE], vh[GE];
+      if (row < p.rows) {
+        const float4* src = reinterpret_cast<const float4*>(p.x + row * GE);
+#pragma unroll
+        for (int i = 0; i < GE / 4; ++i) {
+          const float4 q = __ldg(src + i);
+          v[4 * i] = q.x;
+          v[4 * i + 1] = q.y;
+          v[4 * i + 2] = q.z;
+          v[4 * i + 3] = q.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < GE; ++i) v[i] = 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < GE; ++i) {
+        vh[i] = tf32_hi(v[i]);
+        v[i] -= vh[i];
+      }
+      mbar_wait_relaxed(bars + 8 * B_XEMPTY, (it & 1) ^ 1);     // the pre products of the previous tile are done
+      tc_fence_after();
+      tmem_st32f(tmem + lane_base + kTX, vh);
+      tmem_st32f(tmem + lane_base + kTXlo, v);
+      tmem_wait_st_tc();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 8 * B_XFULL);
+      if (it > 0) write_dx(it - 1);
+      mbar_wait_relaxed(bars + 8 * B_XSFREE, (it & 1) ^ 1);     // the mma.sync phases of the previous tile are done
+#pragma unroll
+      for (int i = 0; i < GE / 2; ++i)
+        *reinterpret_cast<float4*>(xs2 + rl * X2S + 4 * i) = make_float4(vh[2 * i], v[2 * i], vh[2 * i + 1], v[2 * i + 1]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 8 * B_XSFULL);
+    }
+    if (my_tiles > 0) write_dx(my_tiles - 1);
+  } else if (warp == kWarpMma) {
+    // ======================================= MMA issuer =======================================
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc(128, 32);
+      auto issue_pd = [&](uint32_t s) {       // pre = x W1^T and dhid = dout W2 of step s
+        const uint32_t m = s % (uint32_t)n_gen, it = s / (uint32_t)n_gen, wg = s & 1, stage = s % kStages;
+        if (m == 0) mbar_wait_tc(bars + 8 * B_XFULL, it & 1);
+        mbar_wait_tc(bars + 8 * (B_WFULL0 + stage), (s / kStages) & 1);
+        mbar_wait_tc(bars + 8 * (B_DOUTFULL0 + wg), (s >> 1) & 1);
+        tc_fence_after();
+        const uint32_t w = sbase + stage * kImgBytes;
+        const uint32_t twg = tmem + kTWg + kTWgStride * wg;
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {   // x_lo W1_hi, x_hi W1_lo, x_hi W1_hi
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            mma_ts(twg + kTPre, tmem + (pass == 0 ? kTXlo : kTX) + ks * 8,
+                   make_desc(w + kImgW1 + (pass == 1 ? 4096 : 0) + ks * 256, 128, 1024), idesc, (pass | ks) != 0);
+        }
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {   // dout_lo W2_hi, dout_hi W2_lo, dout_hi W2_hi  (K = 16 taps)
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks)
+            mma_ts(twg + kTDhid, twg + (pass == 0 ? kTDoutLo : kTDout) + ks * 8,
+                   make_desc(w + kImgW2T + (pass == 1 ? 2048 : 0) + ks * 256, 128, 512), idesc, (pass | ks) != 0);
+        }
+        mma_commit(bars + 8 * (B_PDFULL0 + wg));
+        if (m == (uint32_t)n_gen - 1) mma_commit(bars + 8 * B_XEMPTY);
+      };
+      auto issue_dx = [&](uint32_t s) {       // dx += dpre W1 of step s
+        const uint32_t m = s % (uint32_t)n_gen, it = s / (uint32_t)n_gen, wg = s & 1, stage = s % kStages;
+        mbar_wait_tc(bars + 8 * (B_DPREFULL0 + wg), (s >> 1) & 1);
+        if (m == 0) mbar_wait_tc(bars + 8 * B_DXEMPTY, (it & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t w = sbase + stage * kImgBytes;
+        const uint32_t twg = tmem + kTWg + kTWgStride * wg;
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {   // dpre_lo W1_hi, dpre_hi W1_lo, dpre_hi W1_hi
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            mma_ts(tmem + kTDx, twg + (pass == 0 ? kTDpreLo : kTDpre) + ks * 8,
+                   make_desc(w + kImgW1T + (pass == 1 ? 4096 : 0) + ks * 256, 128, 1024), idesc, (m | pass | ks) != 0);
+        }
+        mma_commit(bars + 8 * (B_DPREFREE0 + wg));
+        mma_commit(bars + 8 * (B_WEMPTY0 + stage));
+        if (m == (uint32_t)n_gen - 1) mma_commit(bars + 8 * B_DXFULL);
+      };
+      if (total > 0) issue_pd(0);
+      if (total > 1) issue_pd(1);
+      for (uint32_t s = 0; s < total; ++s) {
+        issue_dx(s);
+        if (s + 2 < total) issue_pd(s + 2);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ======================================= weight streamer =======================================
+    if (lane == 0) {
+      for (uint32_t s = 0; s < total; ++s) {
+        const uint32_t stage = s % kStages, m = s % (uint32_t)n_gen;
+        mbar_wait_relaxed(bars + 8 * (B_WEMPTY0 + stage), ((s / kStages) & 1) ^ 1);
+        mbar_expect_tx(bars + 8 * (B_WFULL0 + stage), kImgBytes);
+        tma_load_1d(sbase + stage * kImgBytes, img + (size_t)m * kImgBytes, kImgBytes, bars + 8 * (B_WFULL0 + stage));
+      }
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWarpMma) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+struct DevAttrB {
+  bool done = false;
+  int status = 0;
+};
+DevAttrB g_tcb_attr[64];
+
+}  // namespace
+
+size_t psf_gen_tc_bwd_image_bytes(int n_gen) { return (size_t)n_gen * kImgBytes; }
+
+int psf_gen_tc_bwd(const GenParams& p, void* images, int* grid_out, cudaStream_t st) {
+  if (p.n_gen < 2 || p.L > GLP || p.C > GLP || p.pre != nullptr) return PSF_ERR_UNSUPPORTED;
+  if (reinterpret_cast<uintptr_t>(images) & 127) return PSF_ERR_UNSUPPORTED;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return PSF_ERR_UNSUPPORTED;
+  if (!g_tcb_attr[dev].done) {
+    cudaError_t e = cudaFuncSetAttribute(psf_gen_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBwdTC);
+    g_tcb_attr[dev].status = (int)e;
+    g_tcb_attr[dev].done = true;
+    if (e != cudaSuccess) cudaGetLastError();
+  }
+  if (g_tcb_attr[dev].status != 0) return PSF_ERR_UNSUPPORTED;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long ntiles = (p.rows + 127) >> 7;
+  const long long grid = ntiles < sms ? ntiles : sms;
+  psf_gen_tc_prep_kernel<<<p.n_gen, 256, 0, st>>>(p, (uint8_t*)images);
+  psf_gen_bwd_tc_kernel<<<(unsigned)grid, kThreadsBwd, kSmemBwdTC, st>>>(p, (const uint8_t*)images);
+  *grid_out = (int)grid;
+  return (int)cudaGetLastError();
+}

@@ -13,7 +13,7 @@
 //
 // Arithmetic: kind::tf32 truncates its operands to 10 mantissa bits (measured: tools/microbench/umma_probe.cu), so
 // every product runs as the error-compensated 3xTF32 split  a b ~ a_lo b_hi + a_hi b_lo + a_hi b_hi  with
-// a_hi = a (the hardware ignores the low 13 bits), a_lo = a - trunc(a) (exact in fp32), fp32 accumulation; the small
+// a_hi = a rounded to tf32, a_lo = a - a_hi (exact in fp32), fp32 accumulation; the small
 // terms are issued first so that the accumulator only sees four roundings at full magnitude.  Result: within a few
 // fp32 ulps of the FP32-FMA kernel (psf_gen_sm100.cu), far inside the chain's rtol 1e-5 / atol 1e-6.
 //
@@ -25,7 +25,7 @@
 //   warps 8-11  x loader: global -> registers -> (hi, lo) -> tensor memory
 //   warp 12     TMEM allocation and the single MMA-issuing thread
 #include "psf_gen.cuh"
-#include "psf_ptx.cuh"
+#include "psf_tc.cuh"
 
 namespace {
 
@@ -47,90 +47,6 @@ constexpr uint32_t kSmemTC = kOffBar + 128;
 enum { BAR_XFULL = 0, BAR_XEMPTY, BAR_PREFULL0, BAR_PREFULL1, BAR_PREEMPTY0, BAR_PREEMPTY1, BAR_HIDFULL0, BAR_HIDFULL1,
        BAR_L2DONE0, BAR_L2DONE1, BAR_COUNT };
 
-__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-               : "=r"(ok)
-               : "r"(bar), "r"(parity)
-               : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol error traps (the launch fails with an error) instead of hanging the device.
-__device__ __forceinline__ void mbar_wait_tc(uint32_t bar, uint32_t parity) {
-  if (mbar_try(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();
-  }
-}
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
-  return pred != 0;
-}
-// K-major, no-swizzle canonical layout: 8-row x 16-byte core matrices; LBO = distance of the two 16-byte K chunks of
-// one MMA, SBO = distance of 8-row groups (layout verified by tools/microbench/umma_probe.cu)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo >> 4) & 0x3fff) << 16) |
-         ((uint64_t)((sbo >> 4) & 0x3fff) << 32) | ((uint64_t)1 << 46);
-}
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {  // tf32 x tf32 -> f32, A and B K-major
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d_tmem),
-               "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
-               : "memory");
-}
-__device__ __forceinline__ void mma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_wait_ld_tc() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_wait_st_tc() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld32f(uint32_t taddr, float (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
-        "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]), "=f"(v[17]),
-        "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]), "=f"(v[25]), "=f"(v[26]),
-        "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16f(uint32_t taddr, float (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
-        "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st32f(uint32_t taddr, const float (&v)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-      "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]), "f"(v[10]),
-      "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]), "f"(v[18]), "f"(v[19]), "f"(v[20]),
-      "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]),
-      "f"(v[31])
-      : "memory");
-}
-// the part of v the tensor core drops (it reads the upper 19 bits of a tf32 operand)
-__device__ __forceinline__ float tf32_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
-
-__device__ __forceinline__ float rcp_approx(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 // Exact (erf) GELU, x Phi(x), as  max(x, 0) - |x|/2 * erfcx(|x|/sqrt 2) * exp(-x^2/2)  with
 // erfcx(z) ~ t P6(t), t = 1/(1 + p z): a refit of Abramowitz-Stegun 7.1.26 with one more term (|erf error| < 8e-9 in
 // exact arithmetic); in fp32 the result is within 2.5e-7 absolute of the true value over the whole range - the same
@@ -167,7 +83,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) psf_gen_fwd_tc_kernel(const Gen
     }
     const int r = (m & 3) * 32 + h;
     const uint32_t off = (uint32_t)(m >> 2) * kW1Chunk + (r >> 3) * 1024 + (e >> 2) * 128 + (r & 7) * 16 + (e & 3) * 4;
-    *reinterpret_cast<float*>(smem + off) = v;
+    *reinterpret_cast<float*>(smem + off) = tf32_hi(v);
     *reinterpret_cast<float*>(smem + off + kW1Chunk / 2) = tf32_lo(v);
   }
   for (int idx = tid; idx < n_gen * GLP * GH; idx += kThreadsTC) {
@@ -176,7 +92,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) psf_gen_fwd_tc_kernel(const Gen
     const int Lm = m < p.n_W ? p.L : p.C;
     const float v = l < Lm ? W2[l * GH + h] : 0.f;
     const uint32_t off = kOffW2 + (uint32_t)m * kW2Gen + (l >> 3) * 1024 + (h >> 2) * 128 + (l & 7) * 16 + (h & 3) * 4;
-    *reinterpret_cast<float*>(smem + off) = v;
+    *reinterpret_cast<float*>(smem + off) = tf32_hi(v);
     *reinterpret_cast<float*>(smem + off + kW2Gen / 2) = tf32_lo(v);
   }
   for (int idx = tid; idx < n_gen * GH; idx += kThreadsTC) {
@@ -280,10 +196,15 @@ __global__ void __launch_bounds__(kThreadsTC, 1) psf_gen_fwd_tc_kernel(const Gen
             tmem_ld16f(t_out, o);
             tmem_wait_ld_tc();
           }
-          tmem_st32f(t_hid, v);
+          {
+            float vh[32];
 #pragma unroll
-          for (int h = 0; h < GH; ++h) v[h] = tf32_lo(v[h]);
-          tmem_st32f(t_hid + 32, v);
+            for (int h = 0; h < GH; ++h) vh[h] = tf32_hi(v[h]);
+            tmem_st32f(t_hid, vh);
+#pragma unroll
+            for (int h = 0; h < GH; ++h) v[h] -= vh[h];
+            tmem_st32f(t_hid + 32, v);
+          }
           tmem_wait_st_tc();
           tc_fence_before();
           __syncwarp();
@@ -330,12 +251,17 @@ __global__ void __launch_bounds__(kThreadsTC, 1) psf_gen_fwd_tc_kernel(const Gen
 #pragma unroll
         for (int i = 0; i < GE; ++i) v[i] = 0.f;
       }
-      mbar_wait_tc(bars + 8 * BAR_XEMPTY, (it & 1) ^ 1);   // layer 1 of the previous tile has read x
+      mbar_wait_relaxed(bars + 8 * BAR_XEMPTY, (it & 1) ^ 1);   // layer 1 of the previous tile has read x
       tc_fence_after();
-      tmem_st32f(tmem + lane_base + kColXhi, v);
+      {
+        float vh[32];
 #pragma unroll
-      for (int i = 0; i < GE; ++i) v[i] = tf32_lo(v[i]);
-      tmem_st32f(tmem + lane_base + kColXlo, v);
+        for (int i = 0; i < GE; ++i) vh[i] = tf32_hi(v[i]);
+        tmem_st32f(tmem + lane_base + kColXhi, vh);
+#pragma unroll
+        for (int i = 0; i < GE; ++i) v[i] -= vh[i];
+        tmem_st32f(tmem + lane_base + kColXlo, v);
+      }
       tmem_wait_st_tc();
       tc_fence_before();
       __syncwarp();
