@@ -14,23 +14,30 @@
 //
 // Every product is error-compensated 3xTF32 (psf_gen_tc_sm100.cu); small terms first.
 //
-// Warp roles (448 threads, one CTA per SM, persistent):
-//   warps 0-7   two epilogue warpgroups; consecutive generators alternate between them
-//   warps 8-11  x loader (tensor memory + shared memory) and dx writer
-//   warp 12     tensor-memory allocation + the MMA-issuing thread
-//   warp 13     one thread streaming the per-generator weight images (TMA bulk copies, 4-stage ring)
+// Warp roles (704 threads, one CTA per SM, persistent):
+//   warps 0-15  two epilogue groups of eight warps (two warps per 32 rows, 16 hidden units each); consecutive
+//               generators alternate between the groups
+//   warps 16-19 x loader (tensor memory + shared memory) and dx writer
+//   warp 20     tensor-memory allocation + the MMA-issuing thread
+//   warp 21     one thread streaming the per-generator weight images (TMA bulk copies, 4-stage ring)
 #include "psf_gen.cuh"
 #include "psf_tc.cuh"
 
 namespace {
 
-constexpr int kThreadsBwd = 14 * 32;
-constexpr int kWarpLoad0 = 8, kWarpMma = 12, kWarpTma = 13;
+// timing experiments only (results become wrong): 1 no red.global, 2 no mma.sync loop, 4 no dout loads, 8 no Phi/phi math
+#ifndef PSF_TC_ABLATE
+#define PSF_TC_ABLATE 0
+#endif
+constexpr int kAbl = PSF_TC_ABLATE;
+
+constexpr int kWarpLoad0 = 16, kWarpMma = 20, kWarpTma = 21;
+constexpr int kThreadsBwd = (kWarpTma + 1) * 32;
 constexpr int XS = GE + 4;    // padded row of the staged fp32 tiles (conflict-free fragment loads)
 constexpr int DS = GLP + 4;
 constexpr int X2S = 72;       // row of the (hi, lo)-interleaved x tile, in floats
-// weight image of one generator (bytes): W1 [n=h][k=e] hi, lo | W1^T [n=e][k=h] hi, lo | W2^T [n=h][k=l] hi, lo
-constexpr uint32_t kImgW1 = 0, kImgW1T = 8192, kImgW2T = 16384, kImgBytes = 20480;
+// weight image of one generator (bytes): W1 [n=h][k=e] hi, lo | W1^T [n=e][k=h] hi, lo | W2^T [n=h][k=l] hi, lo | b1 (fp32)
+constexpr uint32_t kImgW1 = 0, kImgW1T = 8192, kImgW2T = 16384, kImgB1 = 20480, kImgBytes = 20736;
 constexpr int kStages = 4;
 // shared memory
 constexpr uint32_t kOffXs = kStages * kImgBytes;                     // [128][X2S] floats
@@ -51,9 +58,11 @@ enum {
 static_assert(B_COUNT * 8 + 8 <= 256, "barrier block");
 
 __device__ __forceinline__ void red_add4g(float* p, float a, float b, float c, float d) {
+  if (kAbl & 1) return;
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 __device__ __forceinline__ void red_add1g(float* p, float a) {
+  if (kAbl & 1) return;
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
 }
 // truncating split for the mma.sync operands (the tensor core ignores the low 13 bits of hi and of lo)
@@ -66,7 +75,7 @@ __device__ __forceinline__ void mma_tf32_sync(float (&d)[4], const uint32_t (&a)
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
-__device__ __forceinline__ void wg_bar(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory"); }
+__device__ __forceinline__ void wg_bar(int wg) { asm volatile("bar.sync %0, 256;" ::"r"(1 + wg) : "memory"); }
 
 // Phi(p) and phi(p) from one exp(-p^2/2): erfc by the 6-term A&S-type fit of psf_gen_tc_sm100.cu (|error| < 1e-7 in fp32)
 __device__ __forceinline__ void normal_cdf_pdf(float p, float& cdf, float& pdf) {
@@ -100,6 +109,7 @@ __global__ void psf_gen_tc_prep_kernel(const GenParams p, uint8_t* __restrict__ 
     *reinterpret_cast<float*>(dst + o2) = tf32_hi(v);
     *reinterpret_cast<float*>(dst + o2 + 4096) = tf32_lo(v);
   }
+  if (threadIdx.x < GH) reinterpret_cast<float*>(dst + kImgB1)[threadIdx.x] = (m < p.n_W ? p.b1 + m * GH : p.gb1)[threadIdx.x];
   for (int idx = threadIdx.x; idx < GLP * GH; idx += blockDim.x) {
     const int l = idx >> 5, h = idx & 31;
     const float v = l < Lm ? W2[l * GH + h] : 0.f;
@@ -122,7 +132,7 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) psf_gen_bwd_tc_kernel(const Ge
     mbar_init(bars + 8 * B_XFULL, 4);
     mbar_init(bars + 8 * B_XEMPTY, 1);
     mbar_init(bars + 8 * B_XSFULL, 4);
-    mbar_init(bars + 8 * B_XSFREE, 8);
+    mbar_init(bars + 8 * B_XSFREE, 16);
     mbar_init(bars + 8 * B_DXFULL, 1);
     mbar_init(bars + 8 * B_DXEMPTY, 4);
     for (int i = 0; i < kStages; ++i) {
@@ -130,9 +140,9 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) psf_gen_bwd_tc_kernel(const Ge
       mbar_init(bars + 8 * (B_WEMPTY0 + i), 1);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(bars + 8 * (B_DOUTFULL0 + i), 4);
+      mbar_init(bars + 8 * (B_DOUTFULL0 + i), 8);
       mbar_init(bars + 8 * (B_PDFULL0 + i), 1);
-      mbar_init(bars + 8 * (B_DPREFULL0 + i), 4);
+      mbar_init(bars + 8 * (B_DPREFULL0 + i), 8);
       mbar_init(bars + 8 * (B_DPREFREE0 + i), 1);
     }
     fence_barrier_init();
@@ -153,9 +163,13 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) psf_gen_bwd_tc_kernel(const Ge
 
   if (warp < kWarpLoad0) {
     // ======================================= epilogue warpgroups =======================================
-    const int wg = warp >> 2, quarter = warp & 3;
+    // warp = (warpgroup, half, quarter): rows 32 quarter .. of the tile (its tensor-memory lanes), hidden units / x columns
+    // 16 half .., taps 8 half ..  Two warps per row halve the registers per thread, which doubles the warps per scheduler
+    // that hide each other's MUFU / HMMA / tensor-memory latencies (the per-thread work is one long dependent chain).
+    const int wg = warp >> 3, half = (warp >> 2) & 1, quarter = warp & 3;
     const int g = lane >> 2, t = lane & 3;
     const int r0 = quarter * 32, rl = r0 + lane;
+    const int c0 = half * 16, t0 = half * 8;
     const uint32_t lane_base = ((uint32_t)quarter * 32u) << 16;
     const uint32_t twg = tmem + lane_base + kTWg + kTWgStride * wg;
     float* dps = reinterpret_cast<float*>(smem + kOffStage + wg * kStageBytes);
@@ -163,117 +177,123 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) psf_gen_bwd_tc_kernel(const Ge
     float* dos = hs + 128 * XS;
     const uint32_t bar_dout = bars + 8 * (B_DOUTFULL0 + wg), bar_pd = bars + 8 * (B_PDFULL0 + wg);
     const uint32_t bar_dpre = bars + 8 * (B_DPREFULL0 + wg), bar_free = bars + 8 * (B_DPREFREE0 + wg);
+    const int pair_id = 3 + wg * 4 + quarter;      // named barrier of the two warps that share the rows
 
     auto row_of = [&](uint32_t s) { return (blockIdx.x + (long long)(s / (uint32_t)n_gen) * gridDim.x) * 128 + rl; };
-    auto load_dout = [&](uint32_t s, float (&d)[GLP]) {
+    auto load_dout = [&](uint32_t s, float (&d)[8]) {      // this warp's 8 taps of its rows
       const int m = (int)(s % (uint32_t)n_gen);
       const long long row = row_of(s);
-      const bool live = row < p.rows;
+      const bool live = row < p.rows && !(kAbl & 4);
       if (m < p.n_W) {
         const float* src = p.Wt + (long long)m * p.sWf + row;
 #pragma unroll
-        for (int l = 0; l < GLP; ++l) d[l] = (live && l < p.L) ? __ldcs(src + (long long)l * p.sWt) : 0.f;
+        for (int i = 0; i < 8; ++i) d[i] = (live && t0 + i < p.L) ? __ldcs(src + (long long)(t0 + i) * p.sWt) : 0.f;
       } else {
         const float* src = p.V + (live ? natural_row(p, row) : 0) * p.C;
 #pragma unroll
-        for (int c = 0; c < GLP; ++c) d[c] = (live && c < p.C) ? __ldcs(src + c) : 0.f;
+        for (int i = 0; i < 8; ++i) d[i] = (live && t0 + i < p.C) ? __ldcs(src + t0 + i) : 0.f;
       }
     };
     // dout -> tensor memory (A operand of dhid = dout W2), hi then lo
-    auto publish_dout = [&](const float (&d)[GLP]) {
-      float hi[GLP], lo[GLP];
+    auto publish_dout = [&](const float (&d)[8]) {
+      float hi[8], lo[8];
 #pragma unroll
-      for (int l = 0; l < GLP; ++l) {
-        hi[l] = tf32_hi(d[l]);
-        lo[l] = d[l] - hi[l];
+      for (int i = 0; i < 8; ++i) {
+        hi[i] = tf32_hi(d[i]);
+        lo[i] = d[i] - hi[i];
       }
-      tmem_st16f(twg + kTDout, hi);
-      tmem_st16f(twg + kTDoutLo, lo);
+      tmem_st8f(twg + kTDout + t0, hi);
+      tmem_st8f(twg + kTDoutLo + t0, lo);
       tmem_wait_st_tc();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_dout);
     };
-    auto stage_dout = [&](const float (&d)[GLP]) {
-#pragma unroll
-      for (int i = 0; i < GLP / 4; ++i)
-        *reinterpret_cast<float4*>(dos + rl * DS + 4 * i) = make_float4(d[4 * i], d[4 * i + 1], d[4 * i + 2], d[4 * i + 3]);
+    auto stage_dout = [&](const float (&d)[8]) {
+      *reinterpret_cast<float4*>(dos + rl * DS + t0) = make_float4(d[0], d[1], d[2], d[3]);
+      *reinterpret_cast<float4*>(dos + rl * DS + t0 + 4) = make_float4(d[4], d[5], d[6], d[7]);
     };
 
-    float dn[GLP];
+    float dn[8], dnn[8];      // dout of this warpgroup's next generator and of the one after (streamed from HBM)
     uint32_t k = 0;
     if ((uint32_t)wg < total) {
       load_dout((uint32_t)wg, dn);
       publish_dout(dn);
       stage_dout(dn);
+      if ((uint32_t)wg + 2 < total) load_dout((uint32_t)wg + 2, dn);
     }
     for (uint32_t s = (uint32_t)wg; s < total; s += 2, ++k) {
       const int m = (int)(s % (uint32_t)n_gen);
       const uint32_t it = s / (uint32_t)n_gen;
       const bool has_next = s + 2 < total;
-      if (has_next) load_dout(s + 2, dn);                 // streamed from HBM a generator ahead
-      const float* b1 = m < p.n_W ? p.b1 + m * GH : p.gb1;
-      float pre[GH], dh[GH];
+      if (s + 4 < total) load_dout(s + 4, dnn);           // two generators ahead: a full iteration to land
+      const float* b1 = reinterpret_cast<const float*>(smem + (s % kStages) * kImgBytes + kImgB1) + c0;   // staged with the weights
+      float pre[16], dh[16];
+      mbar_wait_tc(bars + 8 * (B_WFULL0 + s % kStages), (s / kStages) & 1);   // b1 (TMA write) visible to this thread
       mbar_wait_tc(bar_pd, k & 1);
       tc_fence_after();
-      tmem_ld32f(twg + kTPre, pre);
-      tmem_ld32f(twg + kTDhid, dh);
+      tmem_ld16f(twg + kTPre + c0, pre);
+      tmem_ld16f(twg + kTDhid + c0, dh);
       tmem_wait_ld_tc();
       if (has_next) publish_dout(dn);                     // pre / dhid of the next generator are computed meanwhile
 #pragma unroll
-      for (int h4 = 0; h4 < GH / 4; ++h4) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(b1) + h4);
+      for (int h4 = 0; h4 < 4; ++h4) {
+        const float4 b = *(reinterpret_cast<const float4*>(b1) + h4);
         const float bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int h = 4 * h4 + j;
           const float pv = pre[h] + bb[j];
           float cdf, pdf;
-          normal_cdf_pdf(pv, cdf, pdf);
+          if (kAbl & 8) { cdf = 0.5f; pdf = 0.25f; } else normal_cdf_pdf(pv, cdf, pdf);
           pre[h] = dh[h] * fmaf(pv, pdf, cdf);            // dpre
           dh[h] = pv * cdf;                               // hid
         }
       }
-      // stage for the parameter-gradient products (this warp's rows)
+      // stage for the parameter-gradient products (this warp's rows and columns)
 #pragma unroll
-      for (int i = 0; i < GH / 4; ++i) {
-        *reinterpret_cast<float4*>(dps + rl * XS + 4 * i) = make_float4(pre[4 * i], pre[4 * i + 1], pre[4 * i + 2], pre[4 * i + 3]);
-        *reinterpret_cast<float4*>(hs + rl * XS + 4 * i) = make_float4(dh[4 * i], dh[4 * i + 1], dh[4 * i + 2], dh[4 * i + 3]);
+      for (int i = 0; i < 4; ++i) {
+        *reinterpret_cast<float4*>(dps + rl * XS + c0 + 4 * i) = make_float4(pre[4 * i], pre[4 * i + 1], pre[4 * i + 2], pre[4 * i + 3]);
+        *reinterpret_cast<float4*>(hs + rl * XS + c0 + 4 * i) = make_float4(dh[4 * i], dh[4 * i + 1], dh[4 * i + 2], dh[4 * i + 3]);
       }
       // dpre -> tensor memory (A operand of dx += dpre W1)
       mbar_wait_tc(bar_free, (k & 1) ^ 1);
       tc_fence_after();
       {
 #pragma unroll
-        for (int h = 0; h < GH; ++h) dh[h] = tf32_hi(pre[h]);
-        tmem_st32f(twg + kTDpre, dh);
+        for (int h = 0; h < 16; ++h) dh[h] = tf32_hi(pre[h]);
+        tmem_st16f(twg + kTDpre + c0, dh);
 #pragma unroll
-        for (int h = 0; h < GH; ++h) pre[h] -= dh[h];
-        tmem_st32f(twg + kTDpreLo, pre);
+        for (int h = 0; h < 16; ++h) pre[h] -= dh[h];
+        tmem_st16f(twg + kTDpreLo + c0, pre);
         tmem_wait_st_tc();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_dpre);
       }
       mbar_wait_tc(bars + 8 * B_XSFULL, it & 1);          // x of this tile is in shared memory
-      __syncwarp();
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_id) : "memory");   // the partner's columns of these rows are staged
 
-      // ---- dW1[h][e] += dpre^T x, dW2[l][h] += dout^T hid over this warp's 32 rows (mma.sync m16n8k8, 3xTF32) ----
+      // ---- dW1[h][e] += dpre^T x (this warp: h in its 16 columns), dW2[l][h] += dout^T hid (h in its 16 columns) over
+      //      the warp's 32 rows: mma.sync m16n8k8, 3xTF32 ----
       float* acc_m = wsc + (long long)m * kAccBlk;
-      float d1[2][4][4], d2[4][4];
-#pragma unroll
-      for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) d1[i][j][q] = 0.f;
+      float d1[4][4], d2[2][4];
 #pragma unroll
       for (int j = 0; j < 4; ++j)
 #pragma unroll
+        for (int q = 0; q < 4; ++q) d1[j][q] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
         for (int q = 0; q < 4; ++q) d2[j][q] = 0.f;
 #pragma unroll 1
-      for (int ks = 0; ks < 4; ++ks) {
+      for (int ks = 0; ks < ((kAbl & 2) ? 0 : 4); ++ks) {
         const int ra = r0 + ks * 8 + t, rb = ra + 4;               // rows k = t and k = t + 4 of this step
+        uint32_t ah[4], al[4];                                     // A = dpre[k][h]^T
+        split_trunc(dps[ra * XS + c0 + g], ah[0], al[0]);
+        split_trunc(dps[ra * XS + c0 + g + 8], ah[1], al[1]);
+        split_trunc(dps[rb * XS + c0 + g], ah[2], al[2]);
+        split_trunc(dps[rb * XS + c0 + g + 8], ah[3], al[3]);
         uint32_t bh[4][2], bl[4][2];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {                           // B = x[k][e], pre-split
@@ -285,67 +305,59 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) psf_gen_bwd_tc_kernel(const Ge
           bl[nt][1] = __float_as_uint(vb.y);
         }
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {                           // A = dpre[k][h]^T
-          uint32_t ah[4], al[4];
-          split_trunc(dps[ra * XS + mt * 16 + g], ah[0], al[0]);
-          split_trunc(dps[ra * XS + mt * 16 + g + 8], ah[1], al[1]);
-          split_trunc(dps[rb * XS + mt * 16 + g], ah[2], al[2]);
-          split_trunc(dps[rb * XS + mt * 16 + g + 8], ah[3], al[3]);
+        for (int nt = 0; nt < 4; ++nt) mma_tf32_sync(d1[nt], al, bh[nt]);
 #pragma unroll
-          for (int nt = 0; nt < 4; ++nt) mma_tf32_sync(d1[mt][nt], al, bh[nt]);
+        for (int nt = 0; nt < 4; ++nt) mma_tf32_sync(d1[nt], ah, bl[nt]);
 #pragma unroll
-          for (int nt = 0; nt < 4; ++nt) mma_tf32_sync(d1[mt][nt], ah, bl[nt]);
+        for (int nt = 0; nt < 4; ++nt) mma_tf32_sync(d1[nt], ah, bh[nt]);
+        uint32_t oh[4], ol[4];                                     // A = dout[k][l]^T
+        split_trunc(dos[ra * DS + g], oh[0], ol[0]);
+        split_trunc(dos[ra * DS + g + 8], oh[1], ol[1]);
+        split_trunc(dos[rb * DS + g], oh[2], ol[2]);
+        split_trunc(dos[rb * DS + g + 8], oh[3], ol[3]);
+        uint32_t hh[2][2], hl[2][2];
 #pragma unroll
-          for (int nt = 0; nt < 4; ++nt) mma_tf32_sync(d1[mt][nt], ah, bh[nt]);
-        }
-        uint32_t ah[4], al[4];                                     // A = dout[k][l]^T
-        split_trunc(dos[ra * DS + g], ah[0], al[0]);
-        split_trunc(dos[ra * DS + g + 8], ah[1], al[1]);
-        split_trunc(dos[rb * DS + g], ah[2], al[2]);
-        split_trunc(dos[rb * DS + g + 8], ah[3], al[3]);
-        uint32_t hh[4][2], hl[4][2];
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {                           // B = hid[k][h]
-          split_trunc(hs[ra * XS + nt * 8 + g], hh[nt][0], hl[nt][0]);
-          split_trunc(hs[rb * XS + nt * 8 + g], hh[nt][1], hl[nt][1]);
+        for (int j = 0; j < 2; ++j) {                              // B = hid[k][h]
+          split_trunc(hs[ra * XS + c0 + j * 8 + g], hh[j][0], hl[j][0]);
+          split_trunc(hs[rb * XS + c0 + j * 8 + g], hh[j][1], hl[j][1]);
         }
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) mma_tf32_sync(d2[nt], al, hh[nt]);
+        for (int j = 0; j < 2; ++j) mma_tf32_sync(d2[j], ol, hh[j]);
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) mma_tf32_sync(d2[nt], ah, hl[nt]);
+        for (int j = 0; j < 2; ++j) mma_tf32_sync(d2[j], oh, hl[j]);
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) mma_tf32_sync(d2[nt], ah, hh[nt]);
+        for (int j = 0; j < 2; ++j) mma_tf32_sync(d2[j], oh, hh[j]);
       }
-      {  // bias gradients: column sums over this warp's rows (lane = column)
-        float sb1 = 0.f, sb2 = 0.f;
+      // bias gradients: column sums over the warp's rows (lane = column): db1 by the first half, db2 by the second
+      if (half == 0) {
+        float sb1 = 0.f;
 #pragma unroll 8
-        for (int r = 0; r < 32; ++r) {
-          sb1 += dps[(r0 + r) * XS + lane];
-          sb2 += dos[(r0 + r) * DS + (lane & (GLP - 1))];
-        }
+        for (int r = 0; r < 32; ++r) sb1 += dps[(r0 + r) * XS + lane];
         red_add1g(acc_m + GH * GE + lane, sb1);
+      } else {
+        float sb2 = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) sb2 += dos[(r0 + r) * DS + (lane & (GLP - 1))];
         if (lane < GLP) red_add1g(acc_m + GH * GE + GH + GLP * GH + lane, sb2);
       }
-      // cross-warp sum through shared memory (the dpre / hid tiles are dead once all four warps are here)
+      // cross-warp sum through shared memory (the dpre / hid tiles are dead once all eight warps are here)
       constexpr int PS = 40;
       static_assert(2 * 128 * XS >= 4 * 48 * PS, "partial sums do not fit the dead tiles");
       float* part = dps;
       wg_bar(wg);
       float* mine = part + quarter * 48 * PS;
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          *reinterpret_cast<float2*>(mine + (mt * 16 + g) * PS + nt * 8 + 2 * t) = make_float2(d1[mt][nt][0], d1[mt][nt][1]);
-          *reinterpret_cast<float2*>(mine + (mt * 16 + g + 8) * PS + nt * 8 + 2 * t) = make_float2(d1[mt][nt][2], d1[mt][nt][3]);
-        }
-#pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
-        *reinterpret_cast<float2*>(mine + (32 + g) * PS + nt * 8 + 2 * t) = make_float2(d2[nt][0], d2[nt][1]);
-        *reinterpret_cast<float2*>(mine + (32 + g + 8) * PS + nt * 8 + 2 * t) = make_float2(d2[nt][2], d2[nt][3]);
+        *reinterpret_cast<float2*>(mine + (c0 + g) * PS + nt * 8 + 2 * t) = make_float2(d1[nt][0], d1[nt][1]);
+        *reinterpret_cast<float2*>(mine + (c0 + g + 8) * PS + nt * 8 + 2 * t) = make_float2(d1[nt][2], d1[nt][3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        *reinterpret_cast<float2*>(mine + (32 + g) * PS + c0 + j * 8 + 2 * t) = make_float2(d2[j][0], d2[j][1]);
+        *reinterpret_cast<float2*>(mine + (32 + g + 8) * PS + c0 + j * 8 + 2 * t) = make_float2(d2[j][2], d2[j][3]);
       }
       wg_bar(wg);
-      for (int u = quarter * 32 + lane; u < 48 * 8; u += 128) {
+      for (int u = (warp & 7) * 32 + lane; u < 48 * 8; u += 256) {
         const int prow = u >> 3, col = (u & 7) * 4;
         float4 sum = *reinterpret_cast<const float4*>(part + prow * PS + col);
 #pragma unroll
@@ -364,6 +376,8 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) psf_gen_bwd_tc_kernel(const Ge
         if (lane == 0) mbar_arrive(bars + 8 * B_XSFREE);
       }
       if (has_next) stage_dout(dn);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dn[i] = dnn[i];
     }
   } else if (warp < kWarpMma) {
     // ======================================= x loader / dx writer =======================================
@@ -388,30 +402,33 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) psf_gen_bwd_tc_kernel(const Ge
     };
     for (int it = 0; it < my_tiles; ++it) {
       const long long row = (blockIdx.x + (long long)it * gridDim.x) * 128 + rl;
-      float v[GE], vh[GE];
+      float4 xin[GE / 4];
       if (row < p.rows) {
         const float4* src = reinterpret_cast<const float4*>(p.x + row * GE);
 #pragma unroll
-        for (int i = 0; i < GE / 4; ++i) {
-          const float4 q = __ldg(src + i);
-          v[4 * i] = q.x;
-          v[4 * i + 1] = q.y;
-          v[4 * i + 2] = q.z;
-          v[4 * i + 3] = q.w;
-        }
+        for (int i = 0; i < GE / 4; ++i) xin[i] = __ldg(src + i);
       } else {
 #pragma unroll
-        for (int i = 0; i < GE; ++i) v[i] = 0.f;
-      }
-#pragma unroll
-      for (int i = 0; i < GE; ++i) {
-        vh[i] = tf32_hi(v[i]);
-        v[i] -= vh[i];
+        for (int i = 0; i < GE / 4; ++i) xin[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       mbar_wait_relaxed(bars + 8 * B_XEMPTY, (it & 1) ^ 1);     // the pre products of the previous tile are done
       tc_fence_after();
-      tmem_st32f(tmem + lane_base + kTX, vh);
-      tmem_st32f(tmem + lane_base + kTXlo, v);
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {                           // 16 columns at a time (register pressure)
+        float vh[16], vl[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 q = xin[4 * hf + i];
+          const float e[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            vh[4 * i + j] = tf32_hi(e[j]);
+            vl[4 * i + j] = e[j] - vh[4 * i + j];
+          }
+        }
+        tmem_st16f(tmem + lane_base + kTX + 16 * hf, vh);
+        tmem_st16f(tmem + lane_base + kTXlo + 16 * hf, vl);
+      }
       tmem_wait_st_tc();
       tc_fence_before();
       __syncwarp();
@@ -419,8 +436,12 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) psf_gen_bwd_tc_kernel(const Ge
       if (it > 0) write_dx(it - 1);
       mbar_wait_relaxed(bars + 8 * B_XSFREE, (it & 1) ^ 1);     // the mma.sync phases of the previous tile are done
 #pragma unroll
-      for (int i = 0; i < GE / 2; ++i)
-        *reinterpret_cast<float4*>(xs2 + rl * X2S + 4 * i) = make_float4(vh[2 * i], v[2 * i], vh[2 * i + 1], v[2 * i + 1]);
+      for (int i = 0; i < GE / 4; ++i) {                         // (hi, lo) interleaved for the B fragments of dW1
+        const float4 q = xin[i];
+        const float h0 = tf32_hi(q.x), h1 = tf32_hi(q.y), h2 = tf32_hi(q.z), h3 = tf32_hi(q.w);
+        *reinterpret_cast<float4*>(xs2 + rl * X2S + 8 * i) = make_float4(h0, q.x - h0, h1, q.y - h1);
+        *reinterpret_cast<float4*>(xs2 + rl * X2S + 8 * i + 4) = make_float4(h2, q.z - h2, h3, q.w - h3);
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(bars + 8 * B_XSFULL);
     }

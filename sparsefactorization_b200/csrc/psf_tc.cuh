@@ -12,20 +12,22 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
                : "memory");
   return ok != 0;
 }
-// Bounded waits: a protocol error traps (the launch fails with an error) instead of hanging the device.  try_wait
-// itself suspends the warp for a hardware-defined time, so the loop turns over every ~100 cycles.
+// Bounded waits: a protocol error traps (the launch fails with an error) instead of hanging the device.  A failed
+// try_wait comes back within a few cycles, so every retry backs off with nanosleep: a spinning warp would otherwise take
+// a third of its scheduler's issue slots from the warps doing the work (measured, profiles/r02_gen_notes.md).
 __device__ __forceinline__ void mbar_wait_tc(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try(bar, parity)) {
-    if (++spins > (1u << 24)) __trap();
+    __nanosleep(20);
+    if (++spins > (1u << 26)) __trap();
   }
 }
-// same for warps with slack (loaders): backs off so that it does not take issue slots from the working warps
+// same for warps with slack (loaders)
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try(bar, parity)) {
-    __nanosleep(64);
-    if (++spins > (1u << 24)) __trap();
+    __nanosleep(100);
+    if (++spins > (1u << 25)) __trap();
   }
 }
 __device__ __forceinline__ bool elect_one() {
@@ -89,6 +91,17 @@ __device__ __forceinline__ void tmem_st16f(uint32_t taddr, const float (&v)[16])
       "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]), "f"(v[10]),
       "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
       : "memory");
+}
+__device__ __forceinline__ void tmem_st8f(uint32_t taddr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "f"(v[0]),
+               "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld8f(uint32_t taddr, float (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "r"(taddr)
+               : "memory");
 }
 // 3xTF32 operand split: hi = v rounded to nearest tf32 (stored explicitly - the tensor core would truncate), lo = v - hi
 // (exact; at most 12 significant bits, of which the tensor core keeps 11: the split loses < 2^-24 |v|)
