@@ -8,9 +8,10 @@
 //     dx   [128 x 32] += dpre[128 x 32] . W1          (one accumulator over all generators of the tile)
 //   epilogue warps (thread = row): tcgen05.ld of pre / dhid, Phi / phi, hid = pre Phi, dpre = dhid (Phi + pre phi);
 //     dpre goes back to tensor memory as the A operand of the dx product
-//   warp-level mma.sync (K = rows, so the operands would have to be transposed for tcgen05 - the staged shared-memory
-//     tiles are read as fragments instead): dW1 += dpre^T x, dW2 += dout^T hid over the warp's own 32 rows; the four
-//     warps' partial results are summed through shared memory and added to the CTA's slice of a global workspace
+//   parameter gradients (K = rows: tcgen05 would need the operands transposed, and batching four generators into the
+//     128 lanes does not fit shared / tensor memory - DESIGN.md): dW1 += dpre^T x as FP32 FMA outer products, dW2 += dout^T
+//     hid as warp-level mma.sync 3xTF32 (two different pipes), over the warp's own 32 rows; the four row quarters'
+//     partial results are summed through shared memory and added to the CTA's slice of a global workspace
 //
 // Every product is error-compensated 3xTF32 (psf_gen_tc_sm100.cu); small terms first.
 //
@@ -35,13 +36,12 @@ constexpr int kWarpLoad0 = 16, kWarpMma = 20, kWarpTma = 21;
 constexpr int kThreadsBwd = (kWarpTma + 1) * 32;
 constexpr int XS = GE + 4;    // padded row of the staged fp32 tiles (conflict-free fragment loads)
 constexpr int DS = GLP + 4;
-constexpr int X2S = 72;       // row of the (hi, lo)-interleaved x tile, in floats
 // weight image of one generator (bytes): W1 [n=h][k=e] hi, lo | W1^T [n=e][k=h] hi, lo | W2^T [n=h][k=l] hi, lo | b1 (fp32)
 constexpr uint32_t kImgW1 = 0, kImgW1T = 8192, kImgW2T = 16384, kImgB1 = 20480, kImgBytes = 20736;
 constexpr int kStages = 4;
 // shared memory
-constexpr uint32_t kOffXs = kStages * kImgBytes;                     // [128][X2S] floats
-constexpr uint32_t kOffStage = kOffXs + 128 * X2S * 4;               // per warpgroup: dps, hs, dos
+constexpr uint32_t kOffXs = kStages * kImgBytes;                     // x tile, [128][XS] floats
+constexpr uint32_t kOffStage = kOffXs + 128 * XS * 4;                // per warpgroup: dps, hs, dos
 constexpr uint32_t kStageBytes = (2 * 128 * XS + 128 * DS) * 4;
 constexpr uint32_t kOffBarB = kOffStage + 2 * kStageBytes;
 constexpr uint32_t kSmemBwdTC = kOffBarB + 256;
@@ -74,6 +74,12 @@ __device__ __forceinline__ void mma_tf32_sync(float (&d)[4], const uint32_t (&a)
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void ffma2_tc(float2& c, const float2& a, const float2& b) {
+  unsigned long long* pc = reinterpret_cast<unsigned long long*>(&c);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;"
+      : "+l"(*pc)
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
 }
 __device__ __forceinline__ void wg_bar(int wg) { asm volatile("bar.sync %0, 256;" ::"r"(1 + wg) : "memory"); }
 
@@ -126,7 +132,7 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) psf_gen_bwd_tc_kernel(const Ge
   const uint32_t bars = sbase + kOffBarB;
   uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + kOffBarB + B_COUNT * 8);
   const int n_gen = p.n_gen;
-  float* xs2 = reinterpret_cast<float*>(smem + kOffXs);
+  float* xs = reinterpret_cast<float*>(smem + kOffXs);
 
   if (tid == 0) {
     mbar_init(bars + 8 * B_XFULL, 4);
@@ -277,39 +283,36 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) psf_gen_bwd_tc_kernel(const Ge
       // ---- dW1[h][e] += dpre^T x (this warp: h in its 16 columns), dW2[l][h] += dout^T hid (h in its 16 columns) over
       //      the warp's 32 rows: mma.sync m16n8k8, 3xTF32 ----
       float* acc_m = wsc + (long long)m * kAccBlk;
-      float d1[4][4], d2[2][4];
+      // dW1: lane owns the 4 x 4 block h = c0 + 4 (lane >> 3) .., e = 4 (lane & 7) .. and walks the warp's 32 rows
+      // (FP32 FMA: the legacy mma.sync path costs 16 cycles per m16n8k8 on this part, three of them per product)
+      float2 w1a[4][2];
+      float d2[2][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) d1[j][q] = 0.f;
+      for (int i = 0; i < 4; ++i) w1a[i][0] = w1a[i][1] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int j = 0; j < 2; ++j)
 #pragma unroll
         for (int q = 0; q < 4; ++q) d2[j][q] = 0.f;
-#pragma unroll 1
-      for (int ks = 0; ks < ((kAbl & 2) ? 0 : 4); ++ks) {
-        const int ra = r0 + ks * 8 + t, rb = ra + 4;               // rows k = t and k = t + 4 of this step
-        uint32_t ah[4], al[4];                                     // A = dpre[k][h]^T
-        split_trunc(dps[ra * XS + c0 + g], ah[0], al[0]);
-        split_trunc(dps[ra * XS + c0 + g + 8], ah[1], al[1]);
-        split_trunc(dps[rb * XS + c0 + g], ah[2], al[2]);
-        split_trunc(dps[rb * XS + c0 + g + 8], ah[3], al[3]);
-        uint32_t bh[4][2], bl[4][2];
+      if (!(kAbl & 2)) {
+        const float* dp = dps + r0 * XS + c0 + 4 * (lane >> 3);
+        const float* xp = xs + r0 * XS + 4 * (lane & 7);
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+          const float4 a = *reinterpret_cast<const float4*>(dp + r * XS);
+          const float4 b = *reinterpret_cast<const float4*>(xp + r * XS);
+          const float2 b01 = make_float2(b.x, b.y), b23 = make_float2(b.z, b.w);
+          const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {                           // B = x[k][e], pre-split
-          const float2 va = *reinterpret_cast<const float2*>(xs2 + ra * X2S + 2 * (nt * 8 + g));
-          const float2 vb = *reinterpret_cast<const float2*>(xs2 + rb * X2S + 2 * (nt * 8 + g));
-          bh[nt][0] = __float_as_uint(va.x);
-          bl[nt][0] = __float_as_uint(va.y);
-          bh[nt][1] = __float_as_uint(vb.x);
-          bl[nt][1] = __float_as_uint(vb.y);
+          for (int i = 0; i < 4; ++i) {
+            const float2 aa = make_float2(av[i], av[i]);
+            ffma2_tc(w1a[i][0], aa, b01);
+            ffma2_tc(w1a[i][1], aa, b23);
+          }
         }
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) mma_tf32_sync(d1[nt], al, bh[nt]);
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) mma_tf32_sync(d1[nt], ah, bl[nt]);
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) mma_tf32_sync(d1[nt], ah, bh[nt]);
+      }
+#pragma unroll 1
+      for (int ks = 0; ks < ((kAbl & 2) ? 0 : 4); ++ks) {        // dW2[l][h] += dout^T hid: mma.sync m16n8k8, 3xTF32
+        const int ra = r0 + ks * 8 + t, rb = ra + 4;               // rows k = t and k = t + 4 of this step
         uint32_t oh[4], ol[4];                                     // A = dout[k][l]^T
         split_trunc(dos[ra * DS + g], oh[0], ol[0]);
         split_trunc(dos[ra * DS + g + 8], oh[1], ol[1]);
@@ -347,10 +350,9 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) psf_gen_bwd_tc_kernel(const Ge
       wg_bar(wg);
       float* mine = part + quarter * 48 * PS;
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        *reinterpret_cast<float2*>(mine + (c0 + g) * PS + nt * 8 + 2 * t) = make_float2(d1[nt][0], d1[nt][1]);
-        *reinterpret_cast<float2*>(mine + (c0 + g + 8) * PS + nt * 8 + 2 * t) = make_float2(d1[nt][2], d1[nt][3]);
-      }
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<float4*>(mine + (c0 + 4 * (lane >> 3) + i) * PS + 4 * (lane & 7)) =
+            make_float4(w1a[i][0].x, w1a[i][0].y, w1a[i][1].x, w1a[i][1].y);
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         *reinterpret_cast<float2*>(mine + (32 + g) * PS + c0 + j * 8 + 2 * t) = make_float2(d2[j][0], d2[j][1]);
@@ -436,12 +438,7 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) psf_gen_bwd_tc_kernel(const Ge
       if (it > 0) write_dx(it - 1);
       mbar_wait_relaxed(bars + 8 * B_XSFREE, (it & 1) ^ 1);     // the mma.sync phases of the previous tile are done
 #pragma unroll
-      for (int i = 0; i < GE / 4; ++i) {                         // (hi, lo) interleaved for the B fragments of dW1
-        const float4 q = xin[i];
-        const float h0 = tf32_hi(q.x), h1 = tf32_hi(q.y), h2 = tf32_hi(q.z), h3 = tf32_hi(q.w);
-        *reinterpret_cast<float4*>(xs2 + rl * X2S + 8 * i) = make_float4(h0, q.x - h0, h1, q.y - h1);
-        *reinterpret_cast<float4*>(xs2 + rl * X2S + 8 * i + 4) = make_float4(h2, q.z - h2, h3, q.w - h3);
-      }
+      for (int i = 0; i < GE / 4; ++i) *reinterpret_cast<float4*>(xs + rl * XS + 4 * i) = xin[i];
       __syncwarp();
       if (lane == 0) mbar_arrive(bars + 8 * B_XSFULL);
     }
