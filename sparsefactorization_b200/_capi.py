@@ -75,27 +75,34 @@ _SIGNATURES = {
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 
+def _build_failed_without_nvcc(exc) -> bool:
+    return "nvcc not found" in str(exc)
+
+
 def lib_path() -> str:
     return _build.LIB_PATH
 
 
 def load():
-    """Load (building first if the sources are newer) and type the library."""
+    """Load (rebuilding first if the sources changed since the library was built) and type the library."""
     global _lib
     if _lib is not None:
         return _lib
     with _lock:
         if _lib is not None:
             return _lib
-        path = os.environ.get("PSF_B200_LIB") or _build.LIB_PATH   # override: A/B runs of differently tuned builds
-        if not os.path.exists(path):
+        path = os.environ.get("PSF_B200_LIB")   # override: A/B runs of differently tuned builds
+        if not path:
             try:
-                path = _build.build()
-            except Exception as exc:  # no nvcc on the box and no prebuilt library
-                raise ImportError(
-                    "libpsf_b200.so is missing and could not be built; run "
-                    "`python -m sparsefactorization_b200.build` where nvcc is available. "
-                    "There is no CPU fallback for the PSF chain.") from exc
+                path = _build.build()            # no-op unless the sources changed since the library was built
+            except Exception as exc:             # no nvcc on the box
+                if os.path.exists(_build.LIB_PATH) and _build_failed_without_nvcc(exc):
+                    path = _build.LIB_PATH       # a prebuilt library and no compiler: use it
+                else:
+                    raise ImportError(
+                        "libpsf_b200.so is missing or stale and could not be built; run "
+                        "`python -m sparsefactorization_b200.build` where nvcc is available. "
+                        "There is no CPU fallback for the PSF chain.") from exc
         lib = C.CDLL(path)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(lib, name)   # AttributeError if the header and the library disagree

@@ -133,16 +133,16 @@ class _TapMajorLastLinear(torch.autograd.Function):
             for m in range(n_W):                                          # [BN, L] @ [L, H] -> strided slice
                 torch.mm(dout[m].t(), w[m], out=dh3[:, m, :])
         if ctx.needs_input_grad[1]:
-            kc = _TapMajorLastLinear.KC
-            while BN % kc:
-                kc //= 2
-            S = BN // kc
-            h4 = h2d.view(S, kc, n_W, H)
+            kc = min(_TapMajorLastLinear.KC, BN)
+            S, main = BN // kc, (BN // kc) * kc                           # S full chunks; the remainder separately
+            h4 = h2d[:main].view(S, kc, n_W, H)
             dw = torch.empty_like(w)
             for m in range(n_W):
-                a = dout[m].view(L, S, kc).permute(1, 0, 2)               # [S, L, kc]
+                a = dout[m, :, :main].reshape(L, S, kc).permute(1, 0, 2)  # [S, L, kc]
                 part = torch.bmm(a, h4[:, :, m, :])                       # [S, L, H]
                 torch.sum(part, dim=0, out=dw[m])
+                if main < BN:
+                    dw[m].addmm_(dout[m, :, main:], h2d[main:].view(BN - main, n_W, H)[:, m, :])
         if ctx.needs_input_grad[2]:
             db = dout.sum(-1)
         return dh, dw, db
@@ -242,12 +242,13 @@ class _SkinnyLinear(torch.autograd.Function):
         dy = dy.contiguous()
         rows = x2d.shape[0]
         dx = dy @ w if ctx.needs_input_grad[0] else None
-        kc = _SkinnyLinear.KC
-        while rows % kc:
-            kc //= 2
-        S = rows // kc
-        part = torch.bmm(dy.view(S, kc, -1).transpose(1, 2), x2d.reshape(S, kc, -1))      # [S, E, in]
-        return dx, part.sum(0), dy.sum(0)
+        kc = min(_SkinnyLinear.KC, rows)
+        S, main = rows // kc, (rows // kc) * kc                                            # full chunks + remainder
+        part = torch.bmm(dy[:main].view(S, kc, -1).transpose(1, 2), x2d[:main].reshape(S, kc, -1))   # [S, E, in]
+        dw = part.sum(0)
+        if main < rows:
+            dw = dw + dy[main:].t() @ x2d[main:]
+        return dx, dw, dy.sum(0)
 
 
 def skinny_linear(lin: nn.Linear, x: torch.Tensor) -> torch.Tensor:

@@ -8,7 +8,9 @@ library does not depend on which libcudart torch happens to load.
 """
 from __future__ import annotations
 
+import fcntl
 import glob
+import hashlib
 import os
 import shutil
 import subprocess
@@ -31,12 +33,26 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
+def _source_hash() -> str:
+    """Content hash of everything the library is built from (mtimes do not survive a copy of the tree)."""
+    h = hashlib.sha256()
+    deps = sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + sorted(glob.glob(os.path.join(ROOT, "include", "*.h")))
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def _stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(ROOT, "include", "*.h"))
-    return any(os.path.getmtime(d) > t for d in deps)
+    try:
+        with open(LIB_PATH + ".srchash") as f:
+            return f.read().strip() != _source_hash()
+    except OSError:
+        return True
 
 
 def find_nvcc() -> str:
@@ -47,21 +63,38 @@ def find_nvcc() -> str:
 
 
 def build(force: bool = False, verbose: bool = False, defines=(), out: str = None) -> str:
-    """``defines`` / ``out``: tuning builds (e.g. ``-DPSF2_NW_BWD=6``) written next to the default library and
-    selected at run time with the PSF_B200_LIB environment variable."""
+    """Build (when the sources changed since the last build, or ``force``) and return the library path.
+    ``defines`` / ``out``: tuning builds (e.g. ``-DPSF2_NW_BWD=6``) written next to the default library and
+    selected at run time with the PSF_B200_LIB environment variable.
+    Safe under torchrun: one process builds (file lock), into a temporary file that is renamed into place."""
     out = out or LIB_PATH
-    if not force and out == LIB_PATH and not _stale():
+    default = out == LIB_PATH
+    if not force and default and not _stale():
         return LIB_PATH
     os.makedirs(os.path.dirname(out), exist_ok=True)
-    cmd = [find_nvcc(), *NVCC_FLAGS, *defines, "-I", os.path.join(ROOT, "include"), "-I", CSRC]
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", out, *sources()]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed building libpsf_b200.so")
+    with open(os.path.join(os.path.dirname(out), ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and default and not _stale():       # another rank built it while we waited
+                return LIB_PATH
+            tmp = "{}.tmp.{}".format(out, os.getpid())
+            cmd = [find_nvcc(), *NVCC_FLAGS, *defines, "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+            if verbose:
+                cmd += ["-Xptxas", "-v"]
+            cmd += ["-o", tmp, *sources()]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if verbose or res.returncode != 0:
+                sys.stderr.write(res.stdout + res.stderr)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed building libpsf_b200.so")
+            os.replace(tmp, out)
+            if default:
+                with open(LIB_PATH + ".srchash", "w") as f:
+                    f.write(_source_hash())
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return out
 
 

@@ -59,15 +59,7 @@ namespace {
 #ifndef PSF2_PFW_BWD
 #define PSF2_PFW_BWD 3
 #endif
-// Backward residual accumulator (running sum of G_m over the factors, one quad set per thread and pass) in
-// TENSOR MEMORY instead of an L2-resident global buffer: every thread parks its 32 floats in 32 columns of its
-// own TMEM lane (tcgen05.st / tcgen05.ld, 32x32b shape), which takes the read-modify-write out of the LSU pipe,
-// out of L2 and - since the exchange buffers get written back - out of HBM.  Parity-green on B200, but MEASURED
-// SLOWER (backward 1.54 -> 2.2 ms at B = 132; already with the allocation alone and no TMEM traffic, see
-// profiles/r01_ablation.md), so the default stays 0 = L2-resident global buffer.
-#ifndef PSF2_TMEM_RACC
-#define PSF2_TMEM_RACC 0
-#endif
+// (The tensor-memory variant of the backward residual accumulator measured slower - profiles/r01_ablation.md - and was removed.)
 // timing experiments only (results become wrong): 1 no W loads, 2 no dW stores, 4 no residual traffic,
 // 8 no V_{m-1} loads, 16 no remote operand loads, 32 no state stores, 64 no cluster barrier
 #ifndef PSF2_ABLATE
@@ -214,40 +206,6 @@ __device__ __forceinline__ void stcg4_keep(float* p, const float4& v, unsigned l
                : "memory");
 }
 
-#if PSF2_TMEM_RACC
-// ---- tensor memory as per-thread scratch (32 columns = one quad set of 8 channels) ------------------------
-__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst_u32, uint32_t ncols) {  // one warp
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst_u32), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // the same warp
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float4 (&v)[CT]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-      "f"(v[0].x), "f"(v[0].y), "f"(v[0].z), "f"(v[0].w), "f"(v[1].x), "f"(v[1].y), "f"(v[1].z), "f"(v[1].w),
-      "f"(v[2].x), "f"(v[2].y), "f"(v[2].z), "f"(v[2].w), "f"(v[3].x), "f"(v[3].y), "f"(v[3].z), "f"(v[3].w),
-      "f"(v[4].x), "f"(v[4].y), "f"(v[4].z), "f"(v[4].w), "f"(v[5].x), "f"(v[5].y), "f"(v[5].z), "f"(v[5].w),
-      "f"(v[6].x), "f"(v[6].y), "f"(v[6].z), "f"(v[6].w), "f"(v[7].x), "f"(v[7].y), "f"(v[7].z), "f"(v[7].w)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float4 (&v)[CT]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[0].z), "=f"(v[0].w), "=f"(v[1].x), "=f"(v[1].y), "=f"(v[1].z), "=f"(v[1].w),
-        "=f"(v[2].x), "=f"(v[2].y), "=f"(v[2].z), "=f"(v[2].w), "=f"(v[3].x), "=f"(v[3].y), "=f"(v[3].z), "=f"(v[3].w),
-        "=f"(v[4].x), "=f"(v[4].y), "=f"(v[4].z), "=f"(v[4].w), "=f"(v[5].x), "=f"(v[5].y), "=f"(v[5].z), "=f"(v[5].w),
-        "=f"(v[6].x), "=f"(v[6].y), "=f"(v[6].z), "=f"(v[6].w), "=f"(v[7].x), "=f"(v[7].y), "=f"(v[7].z), "=f"(v[7].w)
-      : "r"(taddr)
-      : "memory");
-}
-
-#endif
 
 __device__ __forceinline__ void red_add4g(float* p, const float4& v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
@@ -479,21 +437,6 @@ __global__ void __launch_bounds__(nw_bwd(LOGJ) * 32, minb_bwd(LOGJ)) psf_chain2_
   uint32_t vparity = 0;
   bool cw_pending = false;
 
-#if PSF2_TMEM_RACC
-  // tensor memory for the residual accumulator: 32 columns per (warp group of 4, pass); power of two >= 32
-  constexpr uint32_t kRaccColsRaw = ((kNW + 3) / 4) * G::NPASS * 32;
-  constexpr uint32_t kRaccCols = kRaccColsRaw <= 32 ? 32 : kRaccColsRaw <= 64 ? 64 : kRaccColsRaw <= 128 ? 128 : kRaccColsRaw <= 256 ? 256 : 512;
-  static_assert(kRaccCols * minb_bwd(LOGJ) <= 512, "tensor memory over-subscribed");
-  const uint32_t tslot = vbar + 16;  // shared-memory word that receives the TMEM base address
-  if (warp == 0) tmem_alloc(tslot, kRaccCols);
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  uint32_t tbase;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tbase) : "r"(tslot) : "memory");
-  // this warp's lane quarter (warp % 4) and column block ((warp / 4) * NPASS + pass) * 32
-  const uint32_t twarp = tbase + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * (G::NPASS * 32u);
-#endif
   // exchange / residual buffers are per CLUSTER (reused sample after sample) so that they stay in L2
   const unsigned long long keep = make_evict_last_policy();
   float* gx0 = p.gx + (long long)cid * plane;
@@ -636,19 +579,12 @@ __global__ void __launch_bounds__(nw_bwd(LOGJ) * 32, minb_bwd(LOGJ)) psf_chain2_
             tap(v, w, k, q * J + js);
           });
           auto issue_tail = [&]() {  // running sum of G_m over the factors (residual): this thread's own rows
-#if PSF2_TMEM_RACC
-            if (p.residual && !first && !(kAbl & 4)) {   // warp-uniform
-              tmem_wait_st();                            // the store of one factor ago (long complete)
-              tmem_ld32(twarp + (uint32_t)pp * 32u, R);  // lands behind the last group of local taps
-            }
-#else
             // the buffer is touched every OTHER factor: an even step adds both G_m (the state) and G_{m-1} (the
             // accumulators it has just finished), so the odd step in between has nothing left to add
             if (p.residual && ((even_step && !first) || (!even_step && last)) && !(kAbl & 4)) {
 #pragma unroll
               for (int ch = 0; ch < CT; ++ch) R[ch] = ldcg4_keep(racc + ch * J + j, keep);
             }
-#endif
           };
           if constexpr (g == 0) {
             if (Q > 1 && cw_pending && !(kAbl & 64)) {
@@ -658,23 +594,6 @@ __global__ void __launch_bounds__(nw_bwd(LOGJ) * 32, minb_bwd(LOGJ)) psf_chain2_
             issue_R(IC<0>{});
           } else if constexpr (g == G::NR + 1) {
             // residual: dV0 also receives G_m of every factor (V_m = W_m V_{m-1} + V_0)
-#if PSF2_TMEM_RACC
-            if (p.residual) {   // warp-uniform: the tensor-memory accesses are warp-collective
-              const uint32_t taddr = twarp + (uint32_t)pp * 32u;
-              if (!first && !(kAbl & 4)) tmem_wait_ld();
-#pragma unroll
-              for (int ch = 0; ch < CT; ++ch) {
-                const float4 own = lds4(state + ch * J + j);
-                if (first) R[ch] = own; else add4(R[ch], own);
-              }
-              if (!last) {
-                if (!(kAbl & 4)) tmem_st32(taddr, R);
-              } else {
-#pragma unroll
-                for (int ch = 0; ch < CT; ++ch) add4(acc[ch], R[ch]);
-              }
-            }
-#else
             if (p.residual && even_step) {
 #pragma unroll
               for (int ch = 0; ch < CT; ++ch) {
@@ -691,7 +610,6 @@ __global__ void __launch_bounds__(nw_bwd(LOGJ) * 32, minb_bwd(LOGJ)) psf_chain2_
 #pragma unroll
               for (int ch = 0; ch < CT; ++ch) add4(acc[ch], R[ch]);
             }
-#endif
           } else if constexpr (g == 1) {
             // ---- head: tap 3 on the previous quad Rq, then taps 0, 1, 2 on (Rq, own quad A) ----
             const float4 w3 = take_w(IC<G::idx_of(3)>{});
@@ -775,12 +693,6 @@ __global__ void __launch_bounds__(nw_bwd(LOGJ) * 32, minb_bwd(LOGJ)) psf_chain2_
       cluster_wait();
     }
   }
-#if PSF2_TMEM_RACC
-  tmem_wait_st();
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tbase, kRaccCols);
-#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -834,14 +746,16 @@ const void* bwd2_kernel_for(int logj, int logq, bool multi = false) {
 int smem2(int logj) { return CT * (1 << logj) * 4 + 64; }
 int threads2(bool bwd, int logj) { return (bwd ? nw_bwd(logj) : nw_fwd(logj)) * 32; }
 
-bool g_attr2_done = false;
-int g_res2[2][10] = {{0}, {0}};  // [bwd][slot]: slots 0..3 = logj 7..10, 4..7 = logj 11 with logq 0..3, 8..9 = logj 12
+std::mutex g_mu2;
+bool g_attr2_done[PSF_MAX_DEVICES] = {};
+int g_res2[PSF_MAX_DEVICES][2][10] = {};  // [device][bwd][slot]: slots 0..3 = logj 7..10, 4..7 = logj 11 with logq 0..3, 8..9 = logj 12
 
-int resident2(bool bwd, int logj, int logq) {
-  int& slot = g_res2[bwd ? 1 : 0][logj < kLogJ ? logj - kLogJMin : (logj == kLogJ ? 4 + logq : 8 + (logq - 3))];
+int resident2(bool bwd, int logj, int logq) {   // caller holds g_mu2
+  const int dev = psf_current_device();
+  if (dev < 0) return 0;
+  int& slot = g_res2[dev][bwd ? 1 : 0][logj < kLogJ ? logj - kLogJMin : (logj == kLogJ ? 4 + logq : 8 + (logq - 3))];
   if (slot > 0) return slot;
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const void* kernel = bwd ? bwd2_kernel_for(logj, logq) : fwd2_kernel_for(logj, logq);
   const int Q = 1 << logq;
@@ -937,7 +851,10 @@ int psf_chain2_plan(const PsfChainArgs& a, PsfFusedPlan* plan) {
     return PSF_ERR_UNSUPPORTED;
   int logj, logq;
   geom2(a, Q, &logj, &logq);
-  if (!g_attr2_done) {
+  const int dev = psf_current_device();
+  if (dev < 0) return PSF_ERR_UNSUPPORTED;
+  std::lock_guard<std::mutex> lock(g_mu2);
+  if (!g_attr2_done[dev]) {
     for (int lj = kLogJMin; lj <= kLogJBig; ++lj)
       for (int lq = (lj == kLogJBig ? 3 : 0); lq < (lj == kLogJBig ? 5 : (lj == kLogJ ? 4 : 1)); ++lq)
         if (cudaFuncSetAttribute(fwd2_kernel_for(lj, lq), cudaFuncAttributeMaxDynamicSharedMemorySize, smem2(lj)) !=
@@ -949,7 +866,7 @@ int psf_chain2_plan(const PsfChainArgs& a, PsfFusedPlan* plan) {
           cudaGetLastError();
           return PSF_ERR_UNSUPPORTED;
         }
-    g_attr2_done = true;
+    g_attr2_done[dev] = true;
   }
   const int rf = resident2(false, logj, logq), rb = resident2(true, logj, logq);
   if (rf < 1 || rb < 1) return PSF_ERR_UNSUPPORTED;

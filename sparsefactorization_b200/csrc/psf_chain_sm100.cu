@@ -671,18 +671,20 @@ int env_int(const char* name, int dflt) {
   return x > 0 ? x : dflt;
 }
 
-bool g_attr_done = false;
+std::mutex g_mu1;
+bool g_attr_done[PSF_MAX_DEVICES] = {};
 
 struct OccCache {
-  int P, threads, smem, clusters;
+  int dev, P, threads, smem, clusters;
   const void* kernel;
 };
 OccCache g_occ[32];
 int g_occ_n = 0;
 
-int resident_clusters(const void* kernel, int P, int threads, int smem, int sms) {
+int resident_clusters(const void* kernel, int P, int threads, int smem, int sms) {   // caller holds g_mu1
+  const int dev = psf_current_device();
   for (int i = 0; i < g_occ_n; ++i)
-    if (g_occ[i].P == P && g_occ[i].threads == threads && g_occ[i].smem == smem && g_occ[i].kernel == kernel)
+    if (g_occ[i].dev == dev && g_occ[i].P == P && g_occ[i].threads == threads && g_occ[i].smem == smem && g_occ[i].kernel == kernel)
       return g_occ[i].clusters;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(P * sms * 2), 1, 1);
@@ -700,7 +702,7 @@ int resident_clusters(const void* kernel, int P, int threads, int smem, int sms)
     cudaGetLastError();
     return 0;
   }
-  if (g_occ_n < 32) g_occ[g_occ_n++] = {P, threads, smem, nclusters, kernel};
+  if (g_occ_n < 32) g_occ[g_occ_n++] = {dev, P, threads, smem, nclusters, kernel};
   return nclusters;
 }
 
@@ -796,8 +798,9 @@ int psf_fused_plan(const PsfChainArgs& a, PsfFusedPlan* plan) {
       a.B > (1 << 20))
     return PSF_ERR_UNSUPPORTED;
   if (a.ws.row != 1 || (a.ws.factor & 3) || (a.ws.sample & 3) || (a.ws.tap & 3)) return PSF_ERR_UNSUPPORTED;
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) != cudaSuccess) return PSF_ERR_UNSUPPORTED;
+  int sms = 148;
+  const int dev = psf_current_device();
+  if (dev < 0) return PSF_ERR_UNSUPPORTED;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   // block rows: 2048 (64 KB state, two CTAs per SM) unless that needs more than 8 CTAs per sample
   int max_rows = env_int("PSF_FUSED_MAX_ROWS", 2048);
@@ -837,7 +840,8 @@ int psf_fused_plan(const PsfChainArgs& a, PsfFusedPlan* plan) {
   plan->smem_bytes = smem_bytes_for(RB, ncw, stages, false);
   plan->smem_bytes_bwd = smem_bytes_for(RB, ncw, stages_b, true);
 
-  if (!g_attr_done) {
+  std::lock_guard<std::mutex> lock(g_mu1);
+  if (!g_attr_done[dev]) {
     const int planes[3] = {512, 2048, 4096};
     for (int q = 0; q < 3; ++q)
       if (cudaFuncSetAttribute(fwd_kernel_for(planes[q]), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
@@ -845,7 +849,7 @@ int psf_fused_plan(const PsfChainArgs& a, PsfFusedPlan* plan) {
           cudaFuncSetAttribute(bwd_kernel_for(planes[q]), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
               cudaSuccess)
         return PSF_ERR_UNSUPPORTED;
-    g_attr_done = true;
+    g_attr_done[dev] = true;
   }
   plan->resident = resident_clusters(fwd_kernel_for(RB), P, threads, plan->smem_bytes, sms);
   plan->resident_bwd = resident_clusters(bwd_kernel_for(RB), P, threads, plan->smem_bytes_bwd, sms);

@@ -1000,7 +1000,8 @@ __global__ void psf_gen_reduce_kernel(const float* __restrict__ ws, int nslices,
   }
 }
 
-bool g_gen_attr = false;
+std::mutex g_gen_mu;
+bool g_gen_attr[PSF_MAX_DEVICES] = {};
 
 // PSF_GEN_TC=0 in the environment keeps the FP32-FMA / mma.sync kernels (A/B timing, parity cross-checks)
 bool gen_use_tc() {
@@ -1026,7 +1027,10 @@ constexpr int kSmemBwd = (3 * kTB * XS + kTB * DS + kBlkBwd) * 4;
 int gen_check(int64_t rows, int n_W, int E, int H, int L) {
   if (E != GE || H != GH || L < 1 || L > GLP || n_W < 1 || rows < 1) return PSF_ERR_UNSUPPORTED;
   if (n_W * kBlkFwd * 4 > 110 * 1024) return PSF_ERR_UNSUPPORTED;  // forward keeps every generator's weights resident
-  if (!g_gen_attr) {
+  const int dev = psf_current_device();
+  if (dev < 0) return PSF_ERR_UNSUPPORTED;
+  std::lock_guard<std::mutex> lock(g_gen_mu);
+  if (!g_gen_attr[dev]) {
     if (cudaFuncSetAttribute(psf_gen_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(psf_gen_bwd_kernel<kTB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBwd) != cudaSuccess ||
         cudaFuncSetAttribute(psf_gen_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBwdMma) != cudaSuccess ||
@@ -1034,7 +1038,7 @@ int gen_check(int64_t rows, int n_W, int E, int H, int L) {
       cudaGetLastError();
       return PSF_ERR_UNSUPPORTED;
     }
-    g_gen_attr = true;
+    g_gen_attr[dev] = true;
   }
   return PSF_OK;
 }

@@ -522,7 +522,7 @@ struct DevAttrB {
   bool done = false;
   int status = 0;
 };
-DevAttrB g_tcb_attr[64];
+DevAttrB g_tcb_attr[PSF_MAX_DEVICES];
 
 }  // namespace
 
@@ -531,13 +531,17 @@ size_t psf_gen_tc_bwd_image_bytes(int n_gen) { return (size_t)n_gen * kImgBytes;
 int psf_gen_tc_bwd(const GenParams& p, void* images, int* grid_out, cudaStream_t st) {
   if (p.n_gen < 2 || p.L > GLP || p.C > GLP || p.pre != nullptr) return PSF_ERR_UNSUPPORTED;
   if (reinterpret_cast<uintptr_t>(images) & 127) return PSF_ERR_UNSUPPORTED;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return PSF_ERR_UNSUPPORTED;
-  if (!g_tcb_attr[dev].done) {
+  const int dev = psf_current_device();
+  if (dev < 0) return PSF_ERR_UNSUPPORTED;
+  {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!g_tcb_attr[dev].done) {
     cudaError_t e = cudaFuncSetAttribute(psf_gen_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBwdTC);
     g_tcb_attr[dev].status = (int)e;
     g_tcb_attr[dev].done = true;
     if (e != cudaSuccess) cudaGetLastError();
+    }
   }
   if (g_tcb_attr[dev].status != 0) return PSF_ERR_UNSUPPORTED;
   int sms = 148;

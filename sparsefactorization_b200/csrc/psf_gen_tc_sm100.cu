@@ -336,19 +336,23 @@ struct DevAttr {
   bool done = false;
   int status = 0;
 };
-DevAttr g_tc_attr[64];   // per device ordinal
+DevAttr g_tc_attr[PSF_MAX_DEVICES];   // per device ordinal
 
 }  // namespace
 
 int psf_gen_tc_fwd(const GenParams& p, cudaStream_t st) {
   if (p.n_gen < 1 || p.n_gen > kMaxGenTC || p.L > GLP || p.C > GLP || p.pre != nullptr) return PSF_ERR_UNSUPPORTED;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return PSF_ERR_UNSUPPORTED;
-  if (!g_tc_attr[dev].done) {
+  const int dev = psf_current_device();
+  if (dev < 0) return PSF_ERR_UNSUPPORTED;
+  {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!g_tc_attr[dev].done) {
     cudaError_t e = cudaFuncSetAttribute(psf_gen_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTC);
     g_tc_attr[dev].status = (int)e;
     g_tc_attr[dev].done = true;
     if (e != cudaSuccess) cudaGetLastError();
+    }
   }
   if (g_tc_attr[dev].status != 0) return PSF_ERR_UNSUPPORTED;
   int sms = 148;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <mutex>
 #include "psf_b200.h"
 
 #define PSF_CUDA_TRY(expr)                       \
@@ -25,6 +26,15 @@ struct PsfChainArgs {
 };
 
 static inline size_t psf_round256(size_t x) { return (x + 255) & ~size_t(255); }
+
+// One-time per-device state (cudaFuncSetAttribute opt-ins, occupancy results) is keyed by the device ordinal and guarded
+// by a mutex: a process may drive several devices from several threads.
+constexpr int PSF_MAX_DEVICES = 64;
+static inline int psf_current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= PSF_MAX_DEVICES) return -1;
+  return d;
+}
 
 // ---- generic (one launch per factor) ----------------------------------------------------
 // W_m points at factor m (sample/row/tap strides apply).  res may be null.

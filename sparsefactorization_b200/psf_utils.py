@@ -31,17 +31,25 @@ def seed_everything(seed=1234):
 
 class DatasetCreator(Dataset):
     """(sample, target) pairs over two indexable containers (psf_utils.py:23-41).
-    ``long_labels=True`` gives the LRA behaviour (labels cast to int64, LRA/psf_utils.py:37)."""
 
-    def __init__(self, data, labels, long_labels=False):
+    Integer targets are returned as int64: the LRA and Genome copies of this class always cast
+    (``LRA/psf_utils.py:37``, ``Genome_Clf/psf_utils.py:37`` - ListOps targets are saved as int32,
+    ``listops_preprocessing.py:54``, and CrossEntropyLoss wants int64), the Synthetic copy never does, and its only
+    integer targets (Temporal Order) are int64 already; floating targets (Adding, MSE) are left alone.
+    ``long_labels=True`` forces the cast, ``False`` forbids it."""
+
+    def __init__(self, data, labels, long_labels=None):
         self.data = data
         self.labels = labels
         self.long_labels = long_labels
 
     def __getitem__(self, index):
         Y = self.labels[index]
-        if self.long_labels:
-            Y = Y.to(dtype=torch.long)
+        cast = self.long_labels
+        if cast is None:
+            cast = torch.is_tensor(Y) and not torch.is_floating_point(Y)
+        if cast:
+            Y = torch.as_tensor(Y).to(dtype=torch.long)
         return (self.data[index], Y)
 
     def __len__(self):
@@ -119,14 +127,15 @@ def _run(net, trainloader, valloader, testloader, n_epochs, test_freq, optimizer
 
 
 def TrainModel(net, trainloader, valloader, testloader, n_epochs, test_freq, optimizer, loss, problem,
-               saving_criteria):
-    """Synthetic tasks (psf_utils.py:48-137).  Returns the per-epoch records it also prints."""
+               saving_criteria, *, clip_grad_norm=None):
+    """Synthetic tasks (psf_utils.py:48-137).  Returns the per-epoch records it also prints.
+    ``clip_grad_norm`` (keyword only, not in the reference signature): max gradient norm, as the Genome loop applies."""
     return _run(net, trainloader, valloader, testloader, n_epochs, test_freq, optimizer, loss, problem,
-                saving_criteria)
+                saving_criteria, clip_grad_norm)
 
 
 def TrainPSF(net, trainloader, valloader, testloader, n_epochs, test_freq, optimizer, loss, problem,
-             saving_criteria):
+             saving_criteria, *, clip_grad_norm=None):
     """LRA tasks (LRA/psf_utils.py:48-128): accuracy is always arg-max."""
     return _run(net, trainloader, valloader, testloader, n_epochs, test_freq, optimizer, loss,
-                problem if problem != 'adding' else 'order', saving_criteria)
+                problem if problem != 'adding' else 'order', saving_criteria, clip_grad_norm)

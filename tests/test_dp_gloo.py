@@ -49,7 +49,8 @@ def _worker(rank, world, port, q):
         lo, hi = dp.shard_range(8)
         opt = torch.optim.SGD(net.parameters(), lr=0.1)
         loss = dp.train_step(net, wrap, opt, torch.nn.MSELoss(), X[lo:hi], Y[lo:hi])
-        grads = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+        assert net.unused.weight.grad is None          # never received a gradient: stays out of the bucket
+        grads = torch.cat([p.grad.reshape(-1) for p in net.parameters() if p.grad is not None])
         params = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
         # TrainModelDP: two epochs on a tiny regression set, metrics all-reduced
         net2 = _make_net()
@@ -78,8 +79,7 @@ def test_two_rank_gradients_equal_single_process_full_batch():
     net = _make_net()
     opt = torch.optim.SGD(net.parameters(), lr=0.1)
     dp.train_step(net, None, opt, torch.nn.MSELoss(), X, Y)
-    ref_grads = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1)
-                           for p in net.parameters()])
+    ref_grads = torch.cat([p.grad.reshape(-1) for p in net.parameters() if p.grad is not None])
     ref_params = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
     for rank, loss, grads, params, hist in res:
         torch.testing.assert_close(torch.tensor(grads), ref_grads, rtol=1e-5, atol=1e-6)
@@ -92,13 +92,45 @@ def test_two_rank_gradients_equal_single_process_full_batch():
 
 def test_shard_range_and_bucket():
     assert dp.shard_range(10, 0, 4) == (0, 2) and dp.shard_range(10, 3, 4) == (6, 8)
+    assert dp.shard_range(10, 3, 4, keep_tail=True) == (6, 10) and dp.shard_range(10, 0, 4, keep_tail=True) == (0, 2)
     net = _make_net()
     b = dp.GradBucket(net.parameters())
-    assert b.flat.numel() == sum(p.numel() for p in net.parameters())
     net(torch.randn(3, 6)).sum().backward()
+    want = torch.cat([p.grad.reshape(-1) for p in net.body.parameters()])
     flat = b.pack().clone()
-    assert float(flat[-12:].abs().sum()) == 0.0        # the unused embedding packs as zeros
+    # only the parameters that received a gradient are in the bucket (decided at the first pack)
+    assert flat.numel() == sum(p.numel() for p in net.body.parameters())
+    torch.testing.assert_close(flat, want)
     b.flat.mul_(2)
     b.unpack()
-    got = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+    got = torch.cat([p.grad.reshape(-1) for p in net.body.parameters()])
     torch.testing.assert_close(got, 2 * flat)
+    assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(b.params, b.views))   # re-pointed, not copied
+    assert net.unused.weight.grad is None
+    # a second step: fresh gradients are copied into the same buffer
+    for p in net.parameters():
+        p.grad = None
+    net(torch.randn(3, 6)).sum().backward()
+    want2 = torch.cat([p.grad.reshape(-1) for p in net.body.parameters()])
+    torch.testing.assert_close(b.pack(), want2)
+
+
+def test_evaluate_counts_the_ragged_tail():
+    torch.manual_seed(0)
+    net = _make_net()
+    X, Y = torch.randn(7, 6), torch.randn(7)
+    loss, acc = dp.evaluate(net, X, Y, torch.nn.MSELoss(), "adding", batch_size=3)     # batches of 3, 3, 1
+    want = float(torch.nn.functional.mse_loss(net(X).squeeze(), Y))
+    assert abs(loss - want) < 1e-6
+
+
+def test_dataset_creator_label_dtypes():
+    from sparsefactorization_b200 import psf_utils
+    from sparsefactorization_b200.genome import psf_utils as genome_utils
+    from sparsefactorization_b200.lra import psf_utils as lra_utils
+    data = torch.zeros(4, 3)
+    assert psf_utils.DatasetCreator(data, torch.arange(4, dtype=torch.int32))[1][1].dtype == torch.long   # ListOps targets
+    assert psf_utils.DatasetCreator(data, torch.rand(4))[1][1].dtype == torch.float32                      # Adding targets
+    assert lra_utils.DatasetCreator(data, torch.arange(4, dtype=torch.int32))[0][1].dtype == torch.long
+    assert genome_utils.DatasetCreator(data, torch.arange(4, dtype=torch.int16))[0][1].dtype == torch.long
+    assert len(lra_utils.DatasetCreator(data, torch.arange(4))) == 4
