@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(kThreadsBwd, 1) psf_gen_bwd_tc_kernel(const Ge
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int h = 4 * h4 + j;
-          const float pv = pre[h] + bb[j];
+          const float pv = tc_unbias(pre[h]) + bb[j];
           float cdf, pdf;
           if (kAbl & 8) { cdf = 0.5f; pdf = 0.25f; } else normal_cdf_pdf(pv, cdf, pdf);
           pre[h] = dh[h] * fmaf(pv, pdf, cdf);            // dpre

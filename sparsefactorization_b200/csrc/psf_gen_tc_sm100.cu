@@ -151,12 +151,12 @@ __global__ void __launch_bounds__(kThreadsTC, 1) psf_gen_fwd_tc_kernel(const Gen
         float* dst = p.Wt + (long long)pend_m * p.sWf + pend_row;
 #pragma unroll
         for (int l = 0; l < GLP; ++l)
-          if (l < p.L) dst[(long long)l * p.sWt] = o[l] + b2[l];
+          if (l < p.L) dst[(long long)l * p.sWt] = tc_unbias(o[l]) + b2[l];
       } else {
         float* dst = p.V + natural_row(p, pend_row) * p.C;
 #pragma unroll
         for (int c = 0; c < GLP; ++c)
-          if (c < p.C) dst[c] = o[c] + b2[c];
+          if (c < p.C) dst[c] = tc_unbias(o[c]) + b2[c];
       }
     };
     for (int it = 0; it < my_tiles; ++it) {
@@ -184,10 +184,10 @@ __global__ void __launch_bounds__(kThreadsTC, 1) psf_gen_fwd_tc_kernel(const Gen
 #pragma unroll
           for (int h4 = 0; h4 < GH / 4; ++h4) {
             const float4 b = *reinterpret_cast<const float4*>(b1 + 4 * h4);
-            v[4 * h4 + 0] = gelu_erf(v[4 * h4 + 0] + b.x);
-            v[4 * h4 + 1] = gelu_erf(v[4 * h4 + 1] + b.y);
-            v[4 * h4 + 2] = gelu_erf(v[4 * h4 + 2] + b.z);
-            v[4 * h4 + 3] = gelu_erf(v[4 * h4 + 3] + b.w);
+            v[4 * h4 + 0] = gelu_erf(tc_unbias(v[4 * h4 + 0]) + b.x);
+            v[4 * h4 + 1] = gelu_erf(tc_unbias(v[4 * h4 + 1]) + b.y);
+            v[4 * h4 + 2] = gelu_erf(tc_unbias(v[4 * h4 + 2]) + b.z);
+            v[4 * h4 + 3] = gelu_erf(tc_unbias(v[4 * h4 + 3]) + b.w);
           }
           float o[16];
           if (pending) {     // the previous generator's layer 2 has finished: its result out, the hid columns free

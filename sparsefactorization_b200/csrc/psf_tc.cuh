@@ -108,6 +108,14 @@ __device__ __forceinline__ void tmem_ld8f(uint32_t taddr, float (&v)[8]) {
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
 __device__ __forceinline__ float tf32_lo(float v) { return v - tf32_hi(v); }
 
+// The tensor core adds into its fp32 accumulator by truncation (measured: tools/microbench/umma_probe.cu,
+// tools/gen_bias_check.py), so a K = 32 product - four full-magnitude accumulations after the small 3xTF32 terms - comes
+// out biased towards zero, where round-to-nearest FMA chains are unbiased: every W shrinks by 1.5e-7 on average (1.7 ulp),
+// and the 14 chained factors add that up coherently (logits of the n = 8192 Temporal Order model off by 2e-6 relative,
+// twice the error of an FP32-FMA evaluation).  Stepping the result one unit in the last place away from zero removes the
+// mean error (measured residual 0.006 ulp on default-initialised generators, rms as the FP32-FMA kernel).
+__device__ __forceinline__ float tc_unbias(float v) { return __uint_as_float(__float_as_uint(v) + 1u); }
+
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -3,9 +3,11 @@
 Replaces the per-factor ``fs[m](data)`` calls and ``g(data)`` of the reference
 (SyntheticExperiments/psf.py:110-126, :165, :175): ``Linear(E,H) -> GELU -> Linear(H,out)`` for every
 W generator and for the V generator, writing W directly in the chain's streaming (tap-major) layout and
-V0 in its natural ``[B, n, C]`` layout.  fp32 FMA arithmetic (no TF32); the backward pass recomputes the
-hidden activations.  Shapes the kernel does not cover (E or H != 32, more than 16 outputs, other layer
-stacks) stay on the batched-GEMM path of ``_psfnet.generate_factors``.  CUDA only.
+V0 in its natural ``[B, n, C]`` layout.  The GEMM-shaped pieces run on the tcgen05 tensor cores as error-compensated
+3xTF32 with the A operands in tensor memory (csrc/psf_gen_tc_sm100.cu, psf_gen_tc_bwd_sm100.cu; ``PSF_GEN_TC=0`` selects
+the FP32-FMA / mma.sync kernels of csrc/psf_gen_sm100.cu); the backward pass recomputes the hidden activations.  Shapes
+the kernels do not cover (E or H != 32, more than 16 outputs, other layer stacks) stay on the batched-GEMM path of
+``_psfnet.generate_factors``.  CUDA only.
 """
 from __future__ import annotations
 
@@ -147,7 +149,7 @@ class _FusedGenerators(torch.autograd.Function):
         with torch.cuda.device(x.device):
             nbytes = int(lib.psf_generators_workspace_bytes(d.n_W))
             ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=x.device)
-            with _Timed("bwd", 2):       # backward kernel + the fixed-order reduction of the per-CTA slices
+            with _Timed("bwd", 3):       # weight-image prep + backward kernel + the fixed-order reduction of the per-CTA slices
                 rc = lib.psf_generators_bwd(C.byref(d), x.data_ptr(), _ptrs((w1, b1, w2, b2)), _ptrs(gs),
                                             dout.data_ptr(), dv0.data_ptr() if ctx.has_g else None,
                                             ctx.pre.data_ptr() if ctx.pre is not None else None, dx.data_ptr(),

@@ -222,6 +222,7 @@ static float round_tf32(float v) {  // round to nearest (ties away), what cvt.rn
 struct Result {
   double err_trunc, err_round, err_full;
   long long cycles;
+  double bias_ulp, rms_ulp;   // (D - exact product of the truncated inputs) * sign(exact) / ulp(exact): mean and rms
 };
 
 static Result run(int N, int K, int a_mn, int b_mn, int a_tmem, int reps, bool split3) {
@@ -259,7 +260,8 @@ static Result run(int N, int K, int a_mn, int b_mn, int a_tmem, int reps, bool s
   long long cyc;
   CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(&cyc, dC, 8, cudaMemcpyDeviceToHost));
-  Result r = {0, 0, 0, cyc};
+  Result r = {0, 0, 0, cyc, 0, 0};
+  double sb = 0, sq = 0;
   for (int m = 0; m < M; ++m)
     for (int n = 0; n < N; ++n) {
       double st = 0, sr = 0, sf = 0;
@@ -272,7 +274,17 @@ static Result run(int N, int K, int a_mn, int b_mn, int a_tmem, int reps, bool s
       r.err_trunc = fmax(r.err_trunc, fabs(d - st));
       r.err_round = fmax(r.err_round, fabs(d - sr));
       r.err_full = fmax(r.err_full, fabs(d - sf));
+      if (reps == 1 && st != 0) {
+        int ex;
+        frexp(st, &ex);
+        const double ulp = ldexp(1.0, ex - 24);
+        const double e = (d - st) / ulp * (st > 0 ? 1.0 : -1.0);
+        sb += e;
+        sq += e * e;
+      }
     }
+  r.bias_ulp = sb / (M * N);
+  r.rms_ulp = sqrt(sq / (M * N));
   cudaFree(dA);
   cudaFree(dB);
   cudaFree(dD);
@@ -291,7 +303,10 @@ int main() {
     int N, K, a_mn, b_mn, a_tm, reps;
     bool split;
   } cases[] = {
+      {"K-major A, K-major B K=8", 32, 8, 0, 0, 0, 1, false},
+      {"K-major A, K-major B K=16", 32, 16, 0, 0, 0, 1, false},
       {"K-major A, K-major B", 32, 32, 0, 0, 0, 1, false},
+      {"K-major A, K-major B K=128", 32, 128, 0, 0, 0, 1, false},
       {"K-major A, K-major B N=240", 240, 32, 0, 0, 0, 1, false},
       {"K-major A, K-major B N=16", 16, 32, 0, 0, 0, 1, false},
       {"K-major A, MN-major B", 32, 32, 0, 1, 0, 1, false},
@@ -315,8 +330,8 @@ int main() {
   for (const Case& c : cases) {
     Result r = run(c.N, c.K, c.a_mn, c.b_mn, c.a_tm, c.reps, c.split);
     const int nmma = c.reps * (c.K / 8) * (c.split ? 3 : 1);
-    printf("%-32s %4d %4d   %d    %d    %d   | %11.3e %11.3e %11.3e | %7lld %7.1f\n", c.name, c.N, c.K, c.a_mn, c.b_mn, c.a_tm,
-           r.err_trunc, r.err_round, r.err_full, r.cycles, (double)r.cycles / nmma);
+    printf("%-32s %4d %4d   %d    %d    %d   | %11.3e %11.3e %11.3e | %7lld %7.1f | bias %+.3f ulp rms %.3f\n", c.name, c.N, c.K, c.a_mn,
+           c.b_mn, c.a_tm, r.err_trunc, r.err_round, r.err_full, r.cycles, (double)r.cycles / nmma, r.bias_ulp, r.rms_ulp);
     fflush(stdout);
   }
   return main2();
