@@ -30,6 +30,19 @@ def test_non_rank0_reference_prints_nothing():
 def test_algorithmic_bytes_match_baseline_md():
     sys.path.insert(0, ROOT)
     import bench
-    fb, bb = bench.alg_bytes_per_seq()
+    fb, bb = bench.Workload("cfg2").alg_bytes_per_seq()
     assert round(fb / 1e6, 3) == 14.811 and round(bb / 1e6, 3) == 29.098
     assert round((fb + bb) / 1e6, 3) == 43.909
+    fb, bb = bench.Workload("cfg3").alg_bytes_per_seq()
+    assert round((fb + bb) / 1e6, 3) == 19.202
+    fb, bb = bench.Workload("cfg4").alg_bytes_per_seq()
+    assert round((fb + bb) / 1e6, 3) == 8.487                                  # cfg4
+
+
+def test_reference_arm_other_config():
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "cfg3", "--steps", "1",
+                          "--warmup", "0", "--ref-batch", "1"], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["config"]["n"] == 8192 and line["metric"].endswith("order_n8192") and line["value"] > 0

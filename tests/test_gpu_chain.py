@@ -93,7 +93,7 @@ def test_sparse_multiply_matches_oracle(dtype, B, n, L, D, offsets):
         assert torch.equal(get_offsets(L).cpu(), torch.tensor([0] + [2 ** k for k in range(L - 1)]))
     Z = SparseMultiply.apply(Fd, Vd, off_arg, 16, 64, 16, 16)
     Z.backward(dZ.to(dev()))
-    tol = dict(rtol=1e-5, atol=1e-5) if dtype == torch.float32 else dict(rtol=1e-12, atol=1e-12)
+    tol = dict(rtol=1e-5, atol=1e-6) if dtype == torch.float32 else dict(rtol=1e-12, atol=1e-12)   # the stated fp32 bar
     np.testing.assert_allclose(Z.detach().cpu().numpy(), want.numpy(), **tol)
     np.testing.assert_allclose(Fd.grad.cpu().numpy(), wdF.numpy(), **tol)
     np.testing.assert_allclose(Vd.grad.cpu().numpy(), wdV.numpy(), **tol)
