@@ -63,4 +63,8 @@ int psf_gen_tc_fwd(const GenParams& p, cudaStream_t st);
 // backward: `images` = psf_gen_tc_bwd_image_bytes(n_gen) bytes of 128-byte aligned device scratch (overwritten); p.ws =
 // zeroed [*grid_out][n_gen][kAccBlk] accumulator slices (the caller reduces them)
 size_t psf_gen_tc_bwd_image_bytes(int n_gen);
+int psf_gen_tc_prep(const GenParams& p, void* images, cudaStream_t st);   // weights -> MMA-ready images (both kernels below)
 int psf_gen_tc_bwd(const GenParams& p, void* images, int* grid_out, cudaStream_t st);
+// second version (psf_gen_tc_bwd2_sm100.cu): parameter gradients on tcgen05 too; whole 128-row tiles only; writes dW1
+// TRANSPOSED ([e][h]) into the accumulator slices
+int psf_gen_tc_bwd2(const GenParams& p, const void* images, int* grid_out, cudaStream_t st);

@@ -974,7 +974,7 @@ struct GenGrads {
   float *gW1, *gb1, *gW2, *gb2; // the V generator (generator index n_W), may be null
 };
 __global__ void psf_gen_reduce_kernel(const float* __restrict__ ws, int nslices, int n_W, int n_gen, int L, int C,
-                                      GenGrads g) {
+                                      GenGrads g, int dw1_transposed = 0) {
   const int total = n_gen * kAccBlk;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     float s = 0.f;
@@ -988,7 +988,7 @@ __global__ void psf_gen_reduce_kernel(const float* __restrict__ ws, int nslices,
     float* db2 = isg ? g.gb2 : g.b2 + m * L;
     const int Lm = isg ? C : L;
     if (o < GH * GE) {
-      dW1[o] = s;
+      dW1[dw1_transposed ? (o & (GH - 1)) * GE + (o >> 5) : o] = s;   // slices hold [e][h] when transposed
     } else if ((o -= GH * GE) < GH) {
       db1[o] = s;
     } else if ((o -= GH) < GLP * GH) {
@@ -1010,6 +1010,15 @@ bool gen_use_tc() {
     return !(e != nullptr && e[0] == '0');
   }();
   return on;
+}
+
+// PSF_GEN_BWD=1 selects the first tcgen05 backward kernel (parameter gradients on FP32 FMA / mma.sync)
+int gen_bwd_version() {
+  static const int v = [] {
+    const char* e = getenv("PSF_GEN_BWD");
+    return e != nullptr ? atoi(e) : 2;
+  }();
+  return v;
 }
 
 int gen_grid(int per_sm) {
@@ -1138,14 +1147,21 @@ int psf_generators_bwd(const psf_gen_desc* d, const float* x, psf_mlp_params fs,
   p.dx = dx;
   p.ws = (float*)workspace;
   p.pre = const_cast<float*>(pre_saved);
-  if (d->rows > 0 && pre_saved == nullptr && gen_use_tc()) {   // tcgen05 / tensor-memory kernel (psf_gen_tc_bwd_sm100.cu)
-    int tc_grid = 0;
-    rc = psf_gen_tc_bwd(p, (char*)workspace + gen_slices_bytes(d->n_W), &tc_grid, st);
+  if (d->rows > 0 && pre_saved == nullptr && gen_use_tc()) {   // tcgen05 / tensor-memory kernels
+    int tc_grid = 0, transposed = 1;
+    void* images = (char*)workspace + gen_slices_bytes(d->n_W);
+    rc = psf_gen_tc_prep(p, images, st);
+    if (rc) return rc;
+    rc = gen_bwd_version() == 1 ? PSF_ERR_UNSUPPORTED : psf_gen_tc_bwd2(p, images, &tc_grid, st);   // all products on tcgen05
+    if (rc == PSF_ERR_UNSUPPORTED) {                              // ragged tiles: parameter gradients on the SIMT pipes
+      transposed = 0;
+      rc = psf_gen_tc_bwd(p, images, &tc_grid, st);
+    }
     if (rc != PSF_ERR_UNSUPPORTED) {
       if (rc) return rc;
       GenGrads gg = {dfs.W1, dfs.b1, dfs.W2, dfs.b2, dg.W1, dg.b1, dg.W2, dg.b2};
       psf_gen_reduce_kernel<<<(p.n_gen * kAccBlk + 255) / 256, 256, 0, st>>>((const float*)workspace, tc_grid, p.n_W, p.n_gen,
-                                                                             p.L, p.C, gg);
+                                                                             p.L, p.C, gg, transposed);
       return (int)cudaGetLastError();
     }
   }

@@ -528,6 +528,11 @@ DevAttrB g_tcb_attr[PSF_MAX_DEVICES];
 
 size_t psf_gen_tc_bwd_image_bytes(int n_gen) { return (size_t)n_gen * kImgBytes; }
 
+int psf_gen_tc_prep(const GenParams& p, void* images, cudaStream_t st) {
+  psf_gen_tc_prep_kernel<<<p.n_gen, 256, 0, st>>>(p, (uint8_t*)images);
+  return (int)cudaGetLastError();
+}
+
 int psf_gen_tc_bwd(const GenParams& p, void* images, int* grid_out, cudaStream_t st) {
   if (p.n_gen < 2 || p.L > GLP || p.C > GLP || p.pre != nullptr) return PSF_ERR_UNSUPPORTED;
   if (reinterpret_cast<uintptr_t>(images) & 127) return PSF_ERR_UNSUPPORTED;
@@ -548,7 +553,6 @@ int psf_gen_tc_bwd(const GenParams& p, void* images, int* grid_out, cudaStream_t
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long ntiles = (p.rows + 127) >> 7;
   const long long grid = ntiles < sms ? ntiles : sms;
-  psf_gen_tc_prep_kernel<<<p.n_gen, 256, 0, st>>>(p, (uint8_t*)images);
   psf_gen_bwd_tc_kernel<<<(unsigned)grid, kThreadsBwd, kSmemBwdTC, st>>>(p, (const uint8_t*)images);
   *grid_out = (int)grid;
   return (int)cudaGetLastError();

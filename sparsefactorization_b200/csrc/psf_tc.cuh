@@ -1,5 +1,6 @@
 // tcgen05 / tensor-memory helpers shared by the generator kernels (sm_100a).
 #pragma once
+#include <stdio.h>
 #include "psf_ptx.cuh"
 
 namespace {
@@ -15,11 +16,23 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
 // Bounded waits: a protocol error traps (the launch fails with an error) instead of hanging the device.  A failed
 // try_wait comes back within a few cycles, so every retry backs off with nanosleep: a spinning warp would otherwise take
 // a third of its scheduler's issue slots from the warps doing the work (measured, profiles/r02_gen_notes.md).
+#ifdef PSF_TC_DEBUG   // name the barrier a protocol error is stuck on (byte offset in shared memory) before trapping
+#define PSF_TC_TIMEOUT(bar, parity) do { if ((threadIdx.x & 31) == 0 || (threadIdx.x >> 5) >= 20) printf("mbarrier timeout: block %d warp %d smem offset %u parity %u\n", blockIdx.x, threadIdx.x >> 5, bar, parity); } while (0)
+#define PSF_TC_SPINS (1u << 23)
+#define PSF_TC_GIVE_UP return      /* keep going so that every stuck warp reports */
+#else
+#define PSF_TC_TIMEOUT(bar, parity)
+#define PSF_TC_SPINS (1u << 26)
+#define PSF_TC_GIVE_UP __trap()
+#endif
 __device__ __forceinline__ void mbar_wait_tc(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try(bar, parity)) {
     __nanosleep(20);
-    if (++spins > (1u << 26)) __trap();
+    if (++spins > PSF_TC_SPINS) {
+      PSF_TC_TIMEOUT(bar, parity);
+      PSF_TC_GIVE_UP;
+    }
   }
 }
 // same for warps with slack (loaders)
@@ -27,7 +40,10 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
   uint32_t spins = 0;
   while (!mbar_try(bar, parity)) {
     __nanosleep(100);
-    if (++spins > (1u << 25)) __trap();
+    if (++spins > PSF_TC_SPINS / 16) {
+      PSF_TC_TIMEOUT(bar, parity);
+      PSF_TC_GIVE_UP;
+    }
   }
 }
 __device__ __forceinline__ bool elect_one() {

@@ -348,6 +348,7 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 struct DiscParams {
+  int layout;       // descriptor layout type of the operand under test: 0 none, 1 = 128B swizzle with 32B base (tf32 MN-major)
   int which;        // 0: operand under test is A (MN-major), 1: B (MN-major), 2: A K-major, 3: B K-major
   uint32_t lbo, sbo;
   int* out;         // per offset bit: [mn, k, count]
@@ -390,7 +391,7 @@ __global__ void __launch_bounds__(128, 1) umma_discover(const DiscParams p) {
     __syncthreads();
     if (warp == 0) {
       if (elect_one()) {
-        const uint64_t td = make_desc(smem_u32(sT), p.lbo, p.sbo);
+        const uint64_t td = make_desc(smem_u32(sT), p.lbo, p.sbo) | ((uint64_t)p.layout << 61);
         const uint64_t id = make_desc(smem_u32(sI), 128, 256);
         const uint32_t idesc = make_idesc(128, 16, testA ? t_mn : 0, testA ? 0 : t_mn);
         if (testA) mma_ss(tD, td, id, idesc, 0);
@@ -494,13 +495,24 @@ int main2() {
   CK(cudaFuncSetAttribute(umma_discover, cudaFuncAttributeMaxDynamicSharedMemorySize, 70 * 1024));
   const char* names[4] = {"A MN-major", "B MN-major", "A K-major", "B K-major"};
   for (int which = 0; which < 4; ++which) {
-    DiscParams p = {which, 8192u, 2048u, dOut, 14};
+    DiscParams p = {0, which, 8192u, 2048u, dOut, 14};
     umma_discover<<<1, 128, 69 * 1024>>>(p);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     int h[64 * 3];
     CK(cudaMemcpy(h, dOut, sizeof(h), cudaMemcpyDeviceToHost));
     printf("discover %s (LBO=8192 SBO=2048): byte offset -> (mn, k) [nonzero count]\n", names[which]);
+    for (int bit = 0; bit <= 14; ++bit)
+      printf("   off %6u -> mn %4d k %3d  [%d]\n", bit == 0 ? 0u : (1u << (bit + 1)), h[bit * 3], h[bit * 3 + 1], h[bit * 3 + 2]);
+  }
+  for (int which = 0; which < 2; ++which) {
+    DiscParams p = {1, which, 16384u, 2048u, dOut, 14};
+    umma_discover<<<1, 128, 69 * 1024>>>(p);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    int h[64 * 3];
+    CK(cudaMemcpy(h, dOut, sizeof(h), cudaMemcpyDeviceToHost));
+    printf("discover %s with layout SWIZZLE_128B_BASE32B (LBO=16384 SBO=2048): byte offset -> (mn, k) [nonzero count]\n", names[which]);
     for (int bit = 0; bit <= 14; ++bit)
       printf("   off %6u -> mn %4d k %3d  [%d]\n", bit == 0 ? 0u : (1u << (bit + 1)), h[bit * 3], h[bit * 3 + 1], h[bit * 3 + 2]);
   }
