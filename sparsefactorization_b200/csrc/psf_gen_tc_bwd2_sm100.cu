@@ -22,31 +22,43 @@
 // XOR-swizzled with the row index, layout type "128B swizzle, 32B base"; probed in tools/microbench/umma_probe.cu).
 // Every product is error-compensated 3xTF32, small terms first (psf_gen_tc_sm100.cu).
 //
-// Warp roles (704 threads, one CTA per SM, persistent over tiles):
+// Warp roles (736 threads, one CTA per SM, persistent over tiles):
 //   warps 0-15   epilogue: thread = (row, 8 hidden units); tcgen05.ld pre / dhid, Phi / phi, dpre -> tensor memory,
 //                [dpre | hid] (hi, lo) -> shared memory B operand, dout -> tensor memory A operand of dhid
 //   warps 16-19  helpers, one per 32-lane quarter: x -> tensor memory / shared memory, dx writer;
 //                warp 16 also builds x^T and drains D lanes 0..31; warps 17 / 18 alternate building dout^T (+ db2) in the
 //                lanes 32..48 / 64..80 and draining them; warp 19 stages the V generator's dV0 (kDsStages steps ahead)
 //   warp 20      tensor-memory allocation + the MMA-issuing thread
-//   warp 21      TMA: weight images (2 stages) and the dout staging tiles (4 stages)
+//   warp 21      TMA: weight images (3 stages);  warp 22  TMA: dout staging tiles (4 stages)
 #include "psf_gen.cuh"
 #include "psf_tc.cuh"
 
 namespace {
 
+// PSF_TC_DEBUG builds record a timeline of block 0 (event, step, SM clock) that tools/gen_timeline.py prints
 #ifdef PSF_TC_DEBUG
-#define DBG(...) do { if ((threadIdx.x & 31) == 0 && blockIdx.x == 0) printf(__VA_ARGS__); } while (0)
+constexpr int kTlPerWarp = 2048;
+__device__ long long g_timeline[24 * kTlPerWarp * 2];
+#define TL_DECL unsigned tl_n = 0
+#define TL(ev, step)                                                                               \
+  do {                                                                                             \
+    if (blockIdx.x == 0 && tl_n < kTlPerWarp) {                                                    \
+      long long* q_ = g_timeline + ((size_t)(threadIdx.x >> 5) * kTlPerWarp + tl_n) * 2;           \
+      q_[0] = (long long)(ev) * 100000 + (long long)(step) + 1;                                    \
+      q_[1] = clock64();                                                                           \
+      ++tl_n;                                                                                      \
+    }                                                                                              \
+  } while (0)
 #else
-#define DBG(...)
+#define TL_DECL
+#define TL(ev, step)
 #endif
 
-constexpr int kEpi = 16, kHelp0 = 16, kMmaW = 20, kTmaW = 21;
-constexpr int kThreads2 = (kTmaW + 1) * 32;
-constexpr int XS2 = GE + 4;                      // padded row of the raw x tile (x^T builder reads columns)
+constexpr int kEpi = 16, kHelp0 = 16, kMmaW = 20, kTmaW = 21, kTmaD = 22;
+constexpr int kThreads2 = (kTmaD + 1) * 32;
 // weight image of one generator (same as psf_gen_tc_bwd_sm100.cu)
 constexpr uint32_t kW1 = 0, kW1T = 8192, kW2T = 16384, kB1 = 20480, kImg = 20736;
-constexpr int kWStages = 2;
+constexpr int kWStages = 3;
 constexpr int kDsStages = 4;
 // shared memory map (bytes)
 constexpr uint32_t kOffB = 0;                                // B operand: 2 buffers x (hi: dpre 16K, hid 16K | lo: 16K, 16K)
@@ -54,8 +66,7 @@ constexpr uint32_t kBBuf = 65536;
 constexpr uint32_t kOffW = kOffB + 2 * kBBuf;                // weight images, kWStages stages
 constexpr uint32_t kOffDs = kOffW + kWStages * kImg;         // dout staging: kDsStages x [16 taps][128 rows] floats
 constexpr uint32_t kDsBuf = 16 * 128 * 4;
-constexpr uint32_t kOffXs2 = kOffDs + kDsStages * kDsBuf;    // raw x tile [128][XS2]
-constexpr uint32_t kOffBar2 = kOffXs2 + 128 * XS2 * 4;
+constexpr uint32_t kOffBar2 = kOffDs + kDsStages * kDsBuf;
 constexpr uint32_t kSmem2 = kOffBar2 + 384;
 static_assert(kSmem2 <= 227 * 1024, "shared memory");
 static_assert(kOffB % 1024 == 0, "B operand alignment (swizzle atoms)");
@@ -64,7 +75,7 @@ constexpr uint32_t cX = 0, cXlo = 32, cDx = 64, cPre = 96, cDhid = 128, cDout = 
                    cD = 448;
 
 enum {
-  Q_XFULL = 0, Q_XEMPTY, Q_XSFULL, Q_XSFREE, Q_ATXFULL, Q_ATXFREE, Q_DXFULL, Q_DXEMPTY,
+  Q_XFULL = 0, Q_XEMPTY, Q_ATXFULL, Q_ATXFREE, Q_DXFULL, Q_DXEMPTY,
   Q_DOUTT, Q_PDFULL, Q_DPREFULL, Q_ATDFULL0, Q_ATDFULL1, Q_GRADDONE0, Q_GRADDONE1, Q_DFREE,
   Q_DSFULL0, Q_DSFREE0 = Q_DSFULL0 + kDsStages, Q_BFULL0 = Q_DSFREE0 + kDsStages, Q_BFREE0 = Q_BFULL0 + 2,
   Q_WFULL0 = Q_BFREE0 + 2, Q_WEMPTY0 = Q_WFULL0 + kWStages, Q_COUNT = Q_WEMPTY0 + kWStages
@@ -105,6 +116,7 @@ __device__ __forceinline__ void normal_cdf_pdf2(float p, float& cdf, float& pdf)
 __global__ void __launch_bounds__(kThreads2, 1) psf_gen_bwd_tc2_kernel(const GenParams p, const uint8_t* __restrict__ img) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  TL_DECL;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bars = sbase + kOffBar2;
   uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + kOffBar2 + Q_COUNT * 8);
@@ -116,13 +128,11 @@ __global__ void __launch_bounds__(kThreads2, 1) psf_gen_bwd_tc2_kernel(const Gen
   if (tid == 0) {
     mbar_init(bar(Q_XFULL), 4);
     mbar_init(bar(Q_XEMPTY), 1);
-    mbar_init(bar(Q_XSFULL), 4);
-    mbar_init(bar(Q_XSFREE), 1);
     mbar_init(bar(Q_ATXFULL), 1);
     mbar_init(bar(Q_ATXFREE), 1);
     mbar_init(bar(Q_DXFULL), 1);
     mbar_init(bar(Q_DXEMPTY), 4);
-    mbar_init(bar(Q_DOUTT), kEpi);
+    mbar_init(bar(Q_DOUTT), 4);
     mbar_init(bar(Q_PDFULL), 1);
     mbar_init(bar(Q_DPREFULL), kEpi);
     mbar_init(bar(Q_ATDFULL0), 1);              // one per dout^T builder warp (they run out of step with each other)
@@ -132,7 +142,7 @@ __global__ void __launch_bounds__(kThreads2, 1) psf_gen_bwd_tc2_kernel(const Gen
     mbar_init(bar(Q_DFREE), 2);
     for (int i = 0; i < kDsStages; ++i) {
       mbar_init(bar(Q_DSFULL0 + i), 1);           // TMA thread (+ bytes); for the V generator the staging warp instead
-      mbar_init(bar(Q_DSFREE0 + i), kEpi + 1);    // the epilogue warps and the step's dout^T builder
+      mbar_init(bar(Q_DSFREE0 + i), 4 + 1);       // the four helpers (dout -> tensor memory) and the step's dout^T builder
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar(Q_BFULL0 + i), kEpi);
@@ -170,38 +180,17 @@ __global__ void __launch_bounds__(kThreads2, 1) psf_gen_bwd_tc2_kernel(const Gen
     const uint32_t boff = (uint32_t)(rl >> 2) * 512 + (uint32_t)(rl & 3) * 128 + (uint32_t)((cq ^ (rl & 3)) * 32);
     const bool swap = (rl >> 2) & 1;                        // which 16-byte half goes first (halves the bank conflicts)
 
-    auto publish_dout = [&](uint32_t s) {                   // dout of step s: staging tile -> tensor memory (hi, lo)
-      const uint32_t b = s % kDsStages;
-      mbar_wait_tc(bar(Q_DSFULL0 + b), (s / kDsStages) & 1);
-      const float* ds = reinterpret_cast<const float*>(smem + kOffDs + b * kDsBuf);
-      float hi[4], lo[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float v = ds[(4 * cq + i) * 128 + rl];
-        hi[i] = tf32_hi(v);
-        lo[i] = v - hi[i];
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(Q_DSFREE0 + b));
-      tmem_st4f(tb + cDout + 4 * cq, hi);
-      tmem_st4f(tb + cDoutLo + 4 * cq, lo);
-      tmem_wait_st_tc();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(Q_DOUTT));
-    };
-
-    if (total > 0) publish_dout(0);
     for (uint32_t s = 0; s < total; ++s) {
       const uint32_t wst = s % kWStages, bbuf = s & 1;
       float pre[8], dh[8];
       mbar_wait_tc(bar(Q_WFULL0 + wst), (s / kWStages) & 1);      // b1 (TMA write) visible to this thread
+      TL(1, s);
       mbar_wait_tc(bar(Q_PDFULL), s & 1);
+      TL(2, s);
       tc_fence_after();
       tmem_ld8f(tb + cPre + 8 * cq, pre);
       tmem_ld8f(tb + cDhid + 8 * cq, dh);
       tmem_wait_ld_tc();
-      if (s + 1 < total) publish_dout(s + 1);              // the next generator's pre / dhid are computed meanwhile
       const float* b1 = reinterpret_cast<const float*>(smem + kOffW + wst * kImg + kB1) + 8 * cq;
 #pragma unroll
       for (int h = 0; h < 8; ++h) {
@@ -220,13 +209,19 @@ __global__ void __launch_bounds__(kThreads2, 1) psf_gen_bwd_tc2_kernel(const Gen
         dh[h] -= hh[h];                                    // hid lo
       }
       // [dpre | hid] (hi, lo) -> the B operand of the gradient product
+      TL(3, s);
       mbar_wait_tc(bar(Q_BFREE0 + bbuf), ((s >> 1) & 1) ^ 1);
+      TL(4, s);
       {
-        uint8_t* bb = smem + kOffB + bbuf * kBBuf + boff;
+        // two 128-bit stores per 32-byte chunk; odd row quads issue the upper half first, so that the eight rows of a warp
+        // that share a swizzle phase spread over both 16-byte slots (4 wavefronts per store instead of 8)
+        const uint32_t bb = sbase + kOffB + bbuf * kBBuf + boff;
+        const uint32_t o1 = swap ? 16u : 0u, o2 = o1 ^ 16u;
         auto put = [&](uint32_t off, const float (&v)[8]) {
-          const float4 a = make_float4(v[0], v[1], v[2], v[3]), b = make_float4(v[4], v[5], v[6], v[7]);
-          *reinterpret_cast<float4*>(bb + off + (swap ? 16 : 0)) = swap ? b : a;
-          *reinterpret_cast<float4*>(bb + off + (swap ? 0 : 16)) = swap ? a : b;
+          const float a0 = swap ? v[4] : v[0], a1 = swap ? v[5] : v[1], a2 = swap ? v[6] : v[2], a3 = swap ? v[7] : v[3];
+          const float c0 = swap ? v[0] : v[4], c1 = swap ? v[1] : v[5], c2 = swap ? v[2] : v[6], c3 = swap ? v[3] : v[7];
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(bb + off + o1), "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(bb + off + o2), "f"(c0), "f"(c1), "f"(c2), "f"(c3) : "memory");
         };
         put(0, ph);             // dpre hi : N group 0
         put(16384, hh);         // hid  hi : N group 1
@@ -244,6 +239,7 @@ __global__ void __launch_bounds__(kThreads2, 1) psf_gen_bwd_tc2_kernel(const Gen
         mbar_arrive(bar(Q_DPREFULL));
         mbar_arrive(bar(Q_BFULL0 + bbuf));
       }
+      TL(5, s);
     }
   } else if (warp < kMmaW) {
     // ================================================ helpers ================================================
@@ -251,7 +247,6 @@ __global__ void __launch_bounds__(kThreads2, 1) psf_gen_bwd_tc2_kernel(const Gen
     const int rl = quarter * 32 + lane;
     const uint32_t lane_base = ((uint32_t)quarter * 32u) << 16;
     const uint32_t tb = tmem + lane_base;
-    float* xs = reinterpret_cast<float*>(smem + kOffXs2);
 
     auto prepare_x = [&](uint32_t it) {                    // x of tile it: tensor memory (lane = row) and shared memory
       const long long row = tile_row0(it) + rl;
@@ -281,24 +276,20 @@ __global__ void __launch_bounds__(kThreads2, 1) psf_gen_bwd_tc2_kernel(const Gen
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(Q_XFULL));
-      mbar_wait_relaxed(bar(Q_XSFREE), (it & 1) ^ 1);      // the x^T builder is done with the previous tile
-#pragma unroll
-      for (int i = 0; i < GE / 4; ++i) *reinterpret_cast<float4*>(xs + rl * XS2 + 4 * i) = xin[i];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(Q_XSFULL));
     };
     auto build_xT = [&](uint32_t it) {                     // warp 16: lane e of A_T <- column e of the x tile (hi, lo)
-      mbar_wait_relaxed(bar(Q_XSFULL), it & 1);
+      const float* xt = p.x + tile_row0(it) * GE + lane;   // 128-byte coalesced row reads (the tile is L2 / L1 resident)
       mbar_wait_relaxed(bar(Q_ATXFREE), (it & 1) ^ 1);     // the previous tile's gradient products have read x^T
       tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         float vh[32], vl[32];
 #pragma unroll
+        for (int r = 0; r < 32; ++r) vl[r] = __ldg(xt + (32 * c + r) * GE);
+#pragma unroll
         for (int r = 0; r < 32; ++r) {
-          const float v = xs[(32 * c + r) * XS2 + lane];
-          vh[r] = tf32_hi(v);
-          vl[r] = v - vh[r];
+          vh[r] = tf32_hi(vl[r]);
+          vl[r] -= vh[r];
         }
         tmem_st32f(tb + cAT + 32 * c, vh);
         tmem_st32f(tb + cATlo + 32 * c, vl);
@@ -306,10 +297,7 @@ __global__ void __launch_bounds__(kThreads2, 1) psf_gen_bwd_tc2_kernel(const Gen
       tmem_wait_st_tc();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(bar(Q_XSFREE));
-        mbar_arrive(bar(Q_ATXFULL));
-      }
+      if (lane == 0) mbar_arrive(bar(Q_ATXFULL));
     };
     auto write_dx = [&](uint32_t it) {
       const long long row = tile_row0(it) + rl;
@@ -326,6 +314,30 @@ __global__ void __launch_bounds__(kThreads2, 1) psf_gen_bwd_tc2_kernel(const Gen
       for (int i = 0; i < GE / 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
     };
 
+    // dout of step s: staging tile -> tensor memory (A operand of dhid = dout W2; lane = row, 16 taps, hi then lo).  Done by
+    // the helpers, off the epilogue's critical path; the region is free once pre / dhid of step s - 1 have been produced.
+    auto publish_dout = [&](uint32_t s) {
+      const uint32_t b = s % kDsStages;
+      if (s > 0) mbar_wait_tc(bar(Q_PDFULL), (s - 1) & 1);
+      mbar_wait_tc(bar(Q_DSFULL0 + b), (s / kDsStages) & 1);
+      tc_fence_after();
+      const float* ds = reinterpret_cast<const float*>(smem + kOffDs + b * kDsBuf);
+      float hi[GLP], lo[GLP];
+#pragma unroll
+      for (int l = 0; l < GLP; ++l) {
+        const float v = ds[l * 128 + rl];
+        hi[l] = tf32_hi(v);
+        lo[l] = v - hi[l];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(Q_DSFREE0 + b));
+      tmem_st16f(tb + cDout, hi);
+      tmem_st16f(tb + cDoutLo, lo);
+      tmem_wait_st_tc();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(Q_DOUTT));
+    };
     // The V generator's dV0 is [rows, C] in natural row order: warp 19 stages it (transposed) into the dout staging ring.
     auto stage_g = [&](uint32_t s1) {
       const uint32_t b1 = s1 % kDsStages, it1 = s1 / (uint32_t)n_gen;
@@ -348,6 +360,7 @@ __global__ void __launch_bounds__(kThreads2, 1) psf_gen_bwd_tc2_kernel(const Gen
       if (quarter == 3 && has_g)
         for (uint32_t s1 = 0; s1 < (uint32_t)kDsStages && s1 < total; ++s1)
           if (s1 % (uint32_t)n_gen >= (uint32_t)p.n_W) stage_g(s1);       // buffers that have not been used yet
+      publish_dout(0);
     }
     for (uint32_t s = 0; s < total; ++s) {
       const uint32_t m = s % (uint32_t)n_gen, it = s / (uint32_t)n_gen;
@@ -360,7 +373,9 @@ __global__ void __launch_bounds__(kThreads2, 1) psf_gen_bwd_tc2_kernel(const Gen
         // ---- dout^T of step s into this warp's A_T lanes (+ the ones lane), db2 ----
         const uint32_t b = s % kDsStages;
         const float* ds = reinterpret_cast<const float*>(smem + kOffDs + b * kDsBuf);
+        TL(10, s);
         mbar_wait_tc(bar(Q_DSFULL0 + b), (s / kDsStages) & 1);
+        TL(11, s);
         const int l = lane & 15;
         float sum = 0.f;
 #pragma unroll 1
@@ -388,11 +403,15 @@ __global__ void __launch_bounds__(kThreads2, 1) psf_gen_bwd_tc2_kernel(const Gen
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(Q_ATDFULL0 + (s & 1)));
+        TL(12, s);
       }
+      if (s + 1 < total) publish_dout(s + 1);              // needs pre / dhid of step s produced (PDFULL)
       if (m == (uint32_t)n_gen - 1 && it + 1 < (uint32_t)my_tiles) prepare_x(it + 1);
       if (quarter == 0 || builder) {
         // ---- drain the gradient accumulator of step s: lanes 0..31 dW1^T (warp 16); the builder's lanes: dW2 and db1 ----
+        TL(13, s);
         mbar_wait_tc(bar(Q_GRADDONE0 + (s & 1)), (s >> 1) & 1);
+        TL(14, s);
         tc_fence_after();
         float v[32];
         tmem_ld32f(tb + cD + (quarter == 0 ? 0 : 32), v);
@@ -418,6 +437,7 @@ __global__ void __launch_bounds__(kThreads2, 1) psf_gen_bwd_tc2_kernel(const Gen
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(Q_DFREE));
+        TL(15, s);
       }
       if (quarter == 3 && has_g) {
         // in step with the pipeline (a parity wait cannot be more than one phase early): once the gradient product of step
@@ -463,7 +483,9 @@ __global__ void __launch_bounds__(kThreads2, 1) psf_gen_bwd_tc2_kernel(const Gen
         const uint32_t m = s % (uint32_t)n_gen, it = s / (uint32_t)n_gen, st = s % kWStages, b = s & 1;
         const bool last = m == (uint32_t)n_gen - 1;
         // ---- dx += dpre W1 (A = dpre, which the epilogue wrote over pre / dhid) ----
+        TL(20, s);
         mbar_wait_tc(bar(Q_DPREFULL), s & 1);
+        TL(21, s);
         if (m == 0) mbar_wait_tc(bar(Q_DXEMPTY), (it & 1) ^ 1);
         tc_fence_after();
         {
@@ -477,12 +499,15 @@ __global__ void __launch_bounds__(kThreads2, 1) psf_gen_bwd_tc2_kernel(const Gen
         }
         mma_commit(bar(Q_WEMPTY0 + st));
         if (last) mma_commit(bar(Q_DXFULL));
+        TL(22, s);
         if (s + 1 < total) issue_pd(s + 1);
+        TL(23, s);
         // ---- D = [x^T ; dout^T ; 1] . [dpre | hid]  (K = the tile's 128 rows) ----
         mbar_wait_tc(bar(Q_BFULL0 + b), (s >> 1) & 1);
         mbar_wait_tc(bar(Q_ATDFULL0 + (s & 1)), (s >> 1) & 1);
         if (m == 0) mbar_wait_tc(bar(Q_ATXFULL), it & 1);
         mbar_wait_tc(bar(Q_DFREE), (s & 1) ^ 1);
+        TL(24, s);
         tc_fence_after();
         {
           const uint32_t bb = sbase + kOffB + b * kBBuf;
@@ -496,26 +521,36 @@ __global__ void __launch_bounds__(kThreads2, 1) psf_gen_bwd_tc2_kernel(const Gen
           }
         }
         mma_commit(bar(Q_GRADDONE0 + (s & 1)));
+        TL(25, s);
         mma_commit(bar(Q_BFREE0 + b));
         if (last) mma_commit(bar(Q_ATXFREE));
       }
     }
     __syncwarp();
-  } else {
-    // ================================================ TMA ================================================
+  } else if (warp == kTmaW) {
+    // ================================================ TMA: weight images ================================================
     if (lane == 0) {
       for (uint32_t s = 0; s < total; ++s) {
-        const uint32_t st = s % kWStages, m = s % (uint32_t)n_gen, it = s / (uint32_t)n_gen, b = s % kDsStages;
+        const uint32_t st = s % kWStages, m = s % (uint32_t)n_gen;
         mbar_wait_relaxed(bar(Q_WEMPTY0 + st), ((s / kWStages) & 1) ^ 1);
         mbar_expect_tx(bar(Q_WFULL0 + st), kImg);
         tma_load_1d(sbase + kOffW + st * kImg, img + (size_t)m * kImg, kImg, bar(Q_WFULL0 + st));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================================ TMA: dout staging ================================================
+    // (its own issuer: dW streams from HBM, so it has to run as far ahead as the staging ring allows, not in step with the
+    // weight ring)
+    if (lane == 0) {
+      for (uint32_t s = 0; s < total; ++s) {
+        const uint32_t m = s % (uint32_t)n_gen, it = s / (uint32_t)n_gen, b = s % kDsStages;
+        if (m >= (uint32_t)p.n_W) continue;                  // the V generator's tile is staged and signalled by warp 19
         mbar_wait_relaxed(bar(Q_DSFREE0 + b), ((s / kDsStages) & 1) ^ 1);
-        if (m < (uint32_t)p.n_W) {       // dW of generator m, rows of this tile: one 512-byte run per tap
-          mbar_expect_tx(bar(Q_DSFULL0 + b), (uint32_t)p.L * 512u);
-          const float* src = p.Wt + (long long)m * p.sWf + tile_row0(it);
-          for (int l = 0; l < p.L; ++l)
-            tma_load_1d(sbase + kOffDs + b * kDsBuf + (uint32_t)l * 512u, src + (long long)l * p.sWt, 512u, bar(Q_DSFULL0 + b));
-        }                                                    // (the V generator's tile is staged and signalled by warp 19)
+        mbar_expect_tx(bar(Q_DSFULL0 + b), (uint32_t)p.L * 512u);   // dW of generator m, this tile: one 512-byte run per tap
+        const float* src = p.Wt + (long long)m * p.sWf + tile_row0(it);
+        for (int l = 0; l < p.L; ++l)
+          tma_load_1d(sbase + kOffDs + b * kDsBuf + (uint32_t)l * 512u, src + (long long)l * p.sWt, 512u, bar(Q_DSFULL0 + b));
       }
     }
     __syncwarp();
@@ -535,6 +570,16 @@ struct DevAttr2 {
 DevAttr2 g_tc2_attr[PSF_MAX_DEVICES];
 
 }  // namespace
+
+#ifdef PSF_TC_DEBUG
+extern "C" int psf_debug_timeline(long long* out) {     // out: 24 warps x kTlPerWarp x (code, clock); code 0 = unused
+  cudaMemcpyFromSymbol(out, g_timeline, sizeof(long long) * 24 * kTlPerWarp * 2);
+  void* sym = nullptr;
+  cudaGetSymbolAddress(&sym, g_timeline);
+  cudaMemset(sym, 0, sizeof(long long) * 24 * kTlPerWarp * 2);
+  return kTlPerWarp;
+}
+#endif
 
 // Shapes the kernel covers: whole 128-row tiles, tap-major dW with 16-byte aligned 512-byte runs per tap.
 int psf_gen_tc_bwd2(const GenParams& p, const void* images, int* grid_out, cudaStream_t st) {

@@ -488,6 +488,87 @@ static void rate_case(long long* dC) {
   printf("      %4d  %d     %d    | %8.1f        %8.1f   (floor %d)\n", N, NACC, ATM, c[0] / 2048.0, c[1] / 2048.0, N / 2);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Sequence probe: the MMA stream of the backward generator kernel (A from tensor memory at changing columns, B either
+// K-major no-swizzle or MN-major SWIZZLE_128B_BASE32B, one accumulator), optionally with NOISE warps that keep
+// tcgen05.ld / tcgen05.st traffic (and shared-memory stores) going on the same SM.
+// ------------------------------------------------------------------------------------------------------------
+template <int N, int BMN, int NOISE>
+__global__ void __launch_bounds__(128 + 512, 1) umma_seq(const RateParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tslot;
+  __shared__ volatile int stop;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = 0.001f * (i & 63);
+  if (tid == 0) {
+    stop = 0;
+    mbar_init(smem_u32(&bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tslot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tD = tslot;
+  long long t0 = 0;
+  if (warp == 0) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc(128, N, 0, BMN);
+      const uint32_t b0 = smem_u32(smem);
+      t0 = clock64();
+      for (int i = 0; i < p.n; i += 16) {
+#pragma unroll
+        for (int ks = 0; ks < 16; ++ks) {
+          const uint64_t bd = BMN ? (make_desc(b0 + ks * 1024, 16384, 512) | ((uint64_t)1 << 61))
+                                  : make_desc(b0 + (ks & 3) * 256 + (ks >> 2) * 4096, 128, 1024);
+          mma_ts(tD, tD + 256 + ks * 8, bd, idesc, 1);
+        }
+      }
+      mma_commit(smem_u32(&bar));
+      p.cycles[1] = clock64() - t0;
+    }
+    __syncwarp();
+    mbar_wait_bounded(smem_u32(&bar), 0);
+    if (t0 != 0) p.cycles[0] = clock64() - t0;
+    stop = 1;
+  } else if (warp >= 4 && NOISE) {
+    // lanes of this warp's quarter, columns 384.. : load, touch, store back (as the epilogue and helper warps do)
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    float v[16];
+    float* sm = reinterpret_cast<float*>(smem + 96 * 1024) + tid * 4;
+    while (!stop) {
+      tmem_ld16(tD + lane_base + 384 + (warp >> 2) * 16, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      for (int j = 0; j < 16; ++j) v[j] = v[j] * 1.0001f + 1.f;
+      if (NOISE > 1) *reinterpret_cast<float4*>(sm) = make_float4(v[0], v[1], v[2], v[3]);
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::
+                   "r"(tD + lane_base + 384 + (warp >> 2) * 16), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]),
+                   "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]) : "memory");
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tD), "r"(512u) : "memory");
+}
+
+template <int N, int BMN, int NOISE>
+static void seq_case(long long* dC) {
+  CK(cudaFuncSetAttribute(umma_seq<N, BMN, NOISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  RateParams p = {2048, dC};
+  umma_seq<N, BMN, NOISE><<<1, 128 + 512, 160 * 1024>>>(p);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  long long c[2];
+  CK(cudaMemcpy(c, dC, 16, cudaMemcpyDeviceToHost));
+  printf("seq   %4d  b_mn %d noise %d | %8.1f        %8.1f   (floor %d)\n", N, BMN, NOISE, c[0] / 2048.0, c[1] / 2048.0, N / 2);
+}
+
 int main2() {
   // layout discovery
   int* dOut;
@@ -530,5 +611,8 @@ int main2() {
   rate_case<32, 1, 1>(dC);  rate_case<32, 4, 1>(dC);
   rate_case<64, 1, 1>(dC);  rate_case<64, 4, 1>(dC);
   rate_case<128, 1, 1>(dC); rate_case<240, 1, 1>(dC);
+  seq_case<32, 0, 0>(dC); seq_case<32, 0, 1>(dC); seq_case<32, 0, 2>(dC);
+  seq_case<64, 1, 0>(dC); seq_case<64, 1, 1>(dC); seq_case<64, 1, 2>(dC);
+  seq_case<64, 0, 0>(dC); seq_case<16, 0, 0>(dC); seq_case<16, 0, 1>(dC);
   return 0;
 }
