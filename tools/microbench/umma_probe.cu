@@ -536,6 +536,18 @@ __global__ void __launch_bounds__(128 + 512, 1) umma_seq(const RateParams p) {
     mbar_wait_bounded(smem_u32(&bar), 0);
     if (t0 != 0) p.cycles[0] = clock64() - t0;
     stop = 1;
+  } else if (warp >= 4 && NOISE == 3) {
+    // ALU-bound neighbours on every scheduler (the epilogue warps of the generator kernels): does the issuing thread starve?
+    float a = (float)tid, b = 1.0001f, c = 0.5f, d = 0.25f;
+    while (!stop) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        a = fmaf(a, b, c);
+        c = fmaf(c, b, d);
+        d = fmaf(d, b, a);
+      }
+    }
+    if (a + c + d == 12345.f) p.cycles[1] = 0;
   } else if (warp >= 4 && NOISE) {
     // lanes of this warp's quarter, columns 384.. : load, touch, store back (as the epilogue and helper warps do)
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
@@ -567,6 +579,68 @@ static void seq_case(long long* dC) {
   long long c[2];
   CK(cudaMemcpy(c, dC, 16, cudaMemcpyDeviceToHost));
   printf("seq   %4d  b_mn %d noise %d | %8.1f        %8.1f   (floor %d)\n", N, BMN, NOISE, c[0] / 2048.0, c[1] / 2048.0, N / 2);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Burst probe: latency of a short dependent chain of MMAs (issue -> commit -> mbarrier completion), which is what the
+// pipelined generator kernels pay per stage (as opposed to the steady-state rate above).
+// ------------------------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(128, 1) umma_burst(int count, int reps, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tslot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 64 * 1024 / 4; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = 0.001f * (i & 63);
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tslot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tD = tslot;
+  if (warp == 0) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc(128, N, 0, 0);
+      const uint32_t b0 = smem_u32(smem);
+      long long issue = 0, done = 0;
+      uint32_t phase = 0;
+      for (int r = 0; r < reps; ++r) {
+        const long long t0 = clock64();
+        for (int i = 0; i < count; ++i)
+          mma_ts(tD, tD + 256 + (i & 3) * 8, make_desc(b0 + (i & 3) * 256, 128, 1024), idesc, i != 0);
+        mma_commit(smem_u32(&bar));
+        const long long t1 = clock64();
+        mbar_wait_bounded(smem_u32(&bar), phase);
+        phase ^= 1;
+        const long long t2 = clock64();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (r > 0) issue += t1 - t0, done += t2 - t0;
+      }
+      out[0] = issue / (reps - 1);
+      out[1] = done / (reps - 1);
+    }
+    __syncwarp();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tD), "r"(512u) : "memory");
+}
+template <int N>
+static void burst_case(long long* dC, int count) {
+  CK(cudaFuncSetAttribute(umma_burst<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  umma_burst<N><<<1, 128, 64 * 1024>>>(count, 9, dC);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  long long c[2];
+  CK(cudaMemcpy(c, dC, 16, cudaMemcpyDeviceToHost));
+  printf("burst N %3d x %2d MMAs | issued after %5lld, complete after %5lld cycles (floor %d)\n", N, count, c[0], c[1], count * N / 2);
 }
 
 int main2() {
@@ -614,5 +688,8 @@ int main2() {
   seq_case<32, 0, 0>(dC); seq_case<32, 0, 1>(dC); seq_case<32, 0, 2>(dC);
   seq_case<64, 1, 0>(dC); seq_case<64, 1, 1>(dC); seq_case<64, 1, 2>(dC);
   seq_case<64, 0, 0>(dC); seq_case<16, 0, 0>(dC); seq_case<16, 0, 1>(dC);
+  seq_case<32, 0, 3>(dC); seq_case<64, 1, 3>(dC);
+  for (int c : {1, 2, 4, 12, 32}) burst_case<32>(dC, c);
+  for (int c : {1, 4, 16, 32}) burst_case<64>(dC, c);
   return 0;
 }
