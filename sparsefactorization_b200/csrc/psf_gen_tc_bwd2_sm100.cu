@@ -415,13 +415,15 @@ __global__ void __launch_bounds__(kThreads2, 1) psf_gen_bwd_tc2_kernel(const Gen
         }
       } else {
         // the V generator: staged row-major [row][C] (the layout of dV0)
-        const float* dv = ds + fl;
+        // taps >= C read a zero word (the padding of tap row 14, which no copy reaches), tap 15 the ones row
+        const float* dv = fl < p.C ? ds + fl : ds + (fl == 15 ? 15 * kDsRow : 14 * kDsRow + 128);
+        const int stride = fl < p.C ? p.C : 0;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           float o[32];
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
-            const float v = fl == 15 ? 1.f : (fl < p.C ? dv[(32 * c + k) * p.C] : 0.f);
+            const float v = dv[(32 * c + k) * stride];
             sum += v;
             const float h = tf32_hi(v);
             o[k] = is_lo ? v - h : h;
@@ -630,30 +632,30 @@ __global__ void __launch_bounds__(kThreads2, 1) psf_gen_bwd_tc2_kernel(const Gen
     // ================================================ TMA: dout staging ================================================
     // (its own issuer: dW streams from HBM, so it has to run as far ahead as the staging ring allows, not in step with the
     // weight ring)
-    if (lane == 0) {
-      for (uint32_t s = 0; s < total; ++s) {
-        const uint32_t m = s % (uint32_t)n_gen, it = s / (uint32_t)n_gen, b = s % kDsStages;
+    // Lane 0 waits for the buffer and announces the bytes; the copies of a tile (one per tap, or one per four rows of an
+    // interleaved dV0) are issued by the lanes side by side, so that the ring never waits for address arithmetic.
+    uint32_t m = 0, it = 0;
+    for (uint32_t s = 0; s < total; ++s) {
+      const uint32_t b = s % kDsStages;
+      const bool is_v = m >= (uint32_t)p.n_W;
+      const uint32_t dst = sbase + kOffDs + b * kDsBuf, full = bar(Q_DSFULL0 + b);
+      if (lane == 0) {
         mbar_wait_relaxed(bar(Q_DSFREE0 + b), ((s / kDsStages) & 1) ^ 1);
-        if (m >= (uint32_t)p.n_W) {
-          // the V generator's dV0 is [rows, C] in natural row order: the tile as it lies (x rows quad-interleaved: one
-          // copy per four rows)
-          const uint32_t dst = sbase + kOffDs + b * kDsBuf;
-          mbar_expect_tx(bar(Q_DSFULL0 + b), (uint32_t)p.C * 512u);
-          if (p.Q <= 1) {
-            tma_load_1d(dst, p.V + tile_row0(it) * p.C, (uint32_t)p.C * 512u, bar(Q_DSFULL0 + b));
-          } else {
-            for (int g4 = 0; g4 < 32; ++g4)
-              tma_load_1d(dst + (uint32_t)g4 * (uint32_t)p.C * 16u, p.V + natural_row(p, tile_row0(it) + 4 * g4) * p.C,
-                          (uint32_t)p.C * 16u, bar(Q_DSFULL0 + b));
-          }
-          continue;
-        }
-        mbar_expect_tx(bar(Q_DSFULL0 + b), (uint32_t)p.L * 512u);   // dW of generator m, this tile: one 512-byte run per tap
-        const float* src = p.Wt + (long long)m * p.sWf + tile_row0(it);
-        for (int l = 0; l < p.L; ++l)
-          tma_load_1d(sbase + kOffDs + b * kDsBuf + (uint32_t)l * (kDsRow * 4u), src + (long long)l * p.sWt, 512u,
-                      bar(Q_DSFULL0 + b));
+        mbar_expect_tx(full, (uint32_t)(is_v ? p.C : p.L) * 512u);
       }
+      __syncwarp();
+      if (!is_v) {
+        // dW of generator m, this tile: one 512-byte run per tap
+        if (lane < p.L)
+          tma_load_1d(dst + (uint32_t)lane * (kDsRow * 4u), p.Wt + (long long)m * p.sWf + (long long)lane * p.sWt + tile_row0(it), 512u, full);
+      } else if (p.Q <= 1) {
+        // the V generator's dV0 is [rows, C] in natural row order: the tile as it lies
+        if (lane == 0) tma_load_1d(dst, p.V + tile_row0(it) * p.C, (uint32_t)p.C * 512u, full);
+      } else {
+        // x rows quad-interleaved: four natural rows are contiguous
+        tma_load_1d(dst + (uint32_t)lane * (uint32_t)p.C * 16u, p.V + natural_row(p, tile_row0(it) + 4 * lane) * p.C, (uint32_t)p.C * 16u, full);
+      }
+      if (++m == (uint32_t)n_gen) m = 0, ++it;
     }
     __syncwarp();
   }

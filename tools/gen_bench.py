@@ -34,6 +34,8 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--gemm", type=int, default=0, help="also time the batched-GEMM route")
     ap.add_argument("--recompute", type=int, default=1, help="1: backward recomputes the pre-activations")
+    ap.add_argument("--g", type=int, default=0, help="1: with the V generator (C = 8 outputs), as inside the model")
+    ap.add_argument("--interleave", type=int, default=1, help="quad-interleave factor of the rows (the model uses 4 at n = 16384)")
     a = ap.parse_args()
     from sparsefactorization_b200 import generators
     generators.SAVE_PREACTIVATIONS = not a.recompute
@@ -44,6 +46,26 @@ def main():
     data = torch.randn(a.B, a.n, 32, device="cuda", requires_grad=True)
     gW = torch.randn(n_W, L, a.B, a.n, device="cuda").permute(0, 2, 3, 1)
     res = {"n": a.n, "B": a.B, "n_W": n_W}
+    if a.g:
+        # the model's call: all W generators and the V generator in one launch each way
+        g = MLPBlock([32, "GELU"], 32, 8).cuda()
+        x2d = data.detach().reshape(a.B * a.n, 32).requires_grad_(True)
+        gV = torch.randn(a.B * a.n, 8, device="cuda")
+        gWt = torch.randn(n_W, L, a.B * a.n, device="cuda")
+        holder = {}
+
+        def fwd_g():
+            holder["o"] = generators.fused_generators(fs, x2d, a.n, a.interleave, g)
+
+        def bwd_g():
+            for p_ in list(fs.parameters()) + list(g.parameters()):
+                p_.grad = None
+            x2d.grad = None
+            torch.autograd.backward(holder["o"], (gWt, gV), retain_graph=True)
+
+        res["with_g"] = {"interleave": a.interleave, "fwd_ms": round(time_ms(fwd_g, a.iters), 3), "bwd_ms": round(time_ms(bwd_g, a.iters), 3)}
+        print(json.dumps(res))
+        return
     for fused in ([True, False] if a.gemm else [True]):
         _psfnet.USE_FUSED_GENERATORS = fused
         holder = {}
