@@ -400,9 +400,11 @@ def run_ours(args):
     gen_flop_bwd = 2.0 * gen_flop + 2.0 * rows * (wl.n_W + 1) * wl.E * 32                              # + recompute
     fused_gen = g_fwd == g_fwd
     if fused_gen:
-        gen_stats = {"kernels": "psf_gen_fwd_tc_kernel / psf_gen_bwd_tc_kernel (tcgen05 + tensor memory, 3xTF32)",
-                     "bound": "forward: MUFU / issue (erf GELU per hidden unit); backward: shared-memory pipe + issue "
-                              "(parameter-gradient products on FP32 FMA and mma.sync) - profiles/r02_gen_notes.md",
+        gen_stats = {"kernels": "psf_gen_fwd_tc_kernel / psf_gen_bwd_tc2_kernel (tcgen05 + tensor memory, 3xTF32; backward: "
+                                "row-local products and parameter gradients all on the tensor pipe)",
+                     "bound": "forward: MUFU / issue (erf GELU per hidden unit); backward: issue slots and barrier latency of the "
+                              "epilogue warps (tensor pipe 36 % busy, about 1.5 k of 4 k cycles per tile-generator) - "
+                              "profiles/r02_gen_notes.md",
                      "fwd_ms": round(g_fwd, 4), "bwd_ms": round(g_bwd, 4),
                      "fwd_TFLOPs": round(gen_flop / g_fwd / 1e9, 2), "bwd_TFLOPs": round(gen_flop_bwd / g_bwd / 1e9, 2),
                      "share_of_step": share(g_fwd + g_bwd)}

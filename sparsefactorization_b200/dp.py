@@ -154,12 +154,13 @@ def evaluate(net, X, Y, loss_fn, problem: str, batch_size: int):
 
 
 def TrainModelDP(net, train_data, val_data, test_data, n_epochs, test_freq, optimizer, loss, problem,
-                 saving_criteria, batch_size, shuffle_seed=0, verbose=True):
+                 saving_criteria, batch_size, shuffle_seed=0, verbose=True, clip_grad_norm=None):
     """Data-parallel counterpart of ``TrainModel``.
 
     ``*_data`` are ``(X, Y)`` tensor pairs holding the FULL dataset on every rank (already on the
     training device); each rank trains on its contiguous shard with per-GPU batch ``batch_size``.
     Rank 0 prints the reference's per-epoch lines and saves the state dict under the same rule.
+    ``clip_grad_norm``: max gradient norm after the all-reduce (the Genome loop clips at 1.0, Genome_Clf/psf_utils.py:73).
     """
     dp = DataParallel(net)
     dp.broadcast_parameters()
@@ -173,7 +174,7 @@ def TrainModelDP(net, train_data, val_data, test_data, n_epochs, test_freq, opti
         running, steps = None, 0
         for i in range(0, Xs.shape[0] - batch_size + 1, batch_size):
             idx = perm[i:i + batch_size]
-            out = train_step(net, dp, optimizer, loss, Xs[idx], Ys[idx])
+            out = train_step(net, dp, optimizer, loss, Xs[idx], Ys[idx], clip_grad_norm)
             running = out if running is None else running + out
             steps += 1
         mean_loss = torch.zeros((), device=Xs.device) if running is None else running / max(steps, 1)

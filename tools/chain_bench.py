@@ -46,7 +46,9 @@ def main():
     a = ap.parse_args()
     n_W = a.n_W or (a.n - 1).bit_length()
     L = n_W + 1
-    dev = torch.device("cuda:0")
+    rank, world = int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))   # under torchrun: replicas
+    dev = torch.device("cuda", rank)
+    torch.cuda.set_device(dev)
     g = torch.Generator(device=dev).manual_seed(0)
     Q = chain.preferred_interleave(n_W, a.B, a.n, L, a.C) if a.gen == 2 and a.path == "auto" else 1
     if a.gen == 1 and a.path == "auto":
@@ -79,7 +81,7 @@ def main():
     used = chain.last_path_used
     t_bwd, _ = time_ms(bwd, a.iters)
     res = {
-        "n": a.n, "B": a.B, "C": a.C, "n_W": n_W, "path": used, "generation": gen, "interleave": Q, "plan": plan,
+        "n": a.n, "B": a.B, "C": a.C, "n_W": n_W, "residual": a.residual, "rank": rank, "world": world, "path": used, "generation": gen, "interleave": Q, "plan": plan,
         "fwd_nograd_ms": round(t_inf, 4), "fwd_ms": round(t_fwd, 4), "bwd_ms": round(t_bwd, 4),
         "fwd_GBps": round(a.B * fb / t_fwd / 1e6, 1), "bwd_GBps": round(a.B * bb / t_bwd / 1e6, 1),
         "fwdbwd_GBps": round(a.B * (fb + bb) / (t_fwd + t_bwd) / 1e6, 1),
