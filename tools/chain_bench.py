@@ -34,7 +34,7 @@ def time_ms(fn, iters, warmup=3):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=16384)
+    ap.add_argument("--n", "--seq-len", dest="n", type=int, default=16384, help="--seq-len: the spelling that survives torchrun's own option parser")
     ap.add_argument("--B", type=int, default=148)
     ap.add_argument("--C", type=int, default=8)
     ap.add_argument("--n_W", type=int, default=0)
