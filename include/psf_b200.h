@@ -183,6 +183,32 @@ int psf_generators_bwd(const psf_gen_desc* d, const float* x, psf_mlp_params fs,
 int psf_chain_fused_plan(const psf_chain_desc* d, int* cluster, int* rows_per_cta, int* threads,
                          int* smem_bytes, int* resident_clusters);
 
+/* ---- Head of the FLATTEN pooling (reference: self.final = nn.Linear(n_vec * n_channels_V, n_class) applied to
+ * V.view(B, -1), SyntheticExperiments/psf.py:60,80; LRA/psf.py:13-22,109; Genome_Clf/psf.py) --------------------------
+ * logits[b][c] = bias[c] + sum_k V[b][k] W[c][k];  V [B,K] row-major, W [n_class,K] (nn.Linear layout), fp32.
+ * Streaming kernels (both directions are HBM-bound passes over V), fixed summation order, no atomics.
+ * Supported: n_class <= PSF_HEAD_MAX_CLASSES, K % 4 == 0, B <= 65535, 16-byte aligned pointers; else
+ * PSF_ERR_UNSUPPORTED and the caller keeps its own GEMM.  bias may be NULL.  The backward pass writes
+ * dV [B,K] and dW [n_class,K] from g = dlogits [B,n_class] (dbias = column sums of g, left to the caller). */
+#define PSF_HEAD_MAX_CLASSES 16
+size_t psf_head_workspace_bytes(int64_t B, int64_t K, int n_class, int backward);
+int psf_head_fwd(const float* V, const float* W, const float* bias, float* out, int64_t B, int64_t K, int n_class,
+                 void* workspace, size_t workspace_bytes, psf_stream_t stream);
+int psf_head_bwd(const float* V, const float* W, const float* g, float* dV, float* dW, int64_t B, int64_t K, int n_class,
+                 void* workspace, size_t workspace_bytes, psf_stream_t stream);
+
+/* ---- init_linear of the Adding model (reference: self.init_linear = nn.Linear(2, embedding_size) applied to the raw
+ * [B, n, 2] input, SyntheticExperiments/psf.py:136-141,155-156) ----------------------------------------------------
+ * y[row][e] = b[e] + sum_i x[row][i] W[e][i];  x [rows, in] row-major, W [out, in] (nn.Linear layout), fp32.
+ * Supported: in <= 4, out % 4 == 0, out <= 128 with 256 % (out / 4) == 0; else PSF_ERR_UNSUPPORTED.
+ * Backward: dW [out, in] and db [out] (may be NULL) from dy [rows, out]; the raw input takes no gradient.
+ * Fixed summation order, no atomics. */
+size_t psf_init_linear_workspace_bytes(int64_t rows, int in_features, int out_features);
+int psf_init_linear_fwd(const float* x, const float* W, const float* b, float* y, int64_t rows, int in_features,
+                        int out_features, psf_stream_t stream);
+int psf_init_linear_bwd(const float* x, const float* dy, float* dW, float* db, int64_t rows, int in_features,
+                        int out_features, void* workspace, size_t workspace_bytes, psf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,15 @@ _SIGNATURES = {
                                      C.c_void_p, C.c_void_p, MlpPtrs, MlpPtrs, C.c_void_p, C.c_size_t, C.c_void_p]),
     "psf_chain_fused_plan": (C.c_int, [C.POINTER(ChainDesc), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                        C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "psf_init_linear_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
+    "psf_init_linear_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
+    "psf_init_linear_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_size_t, C.c_void_p]),
+    "psf_head_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int, C.c_int]),
+    "psf_head_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int,
+                               C.c_void_p, C.c_size_t, C.c_void_p]),
+    "psf_head_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int,
+                               C.c_void_p, C.c_size_t, C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -4,6 +4,8 @@ the fused chain call.  The public, reference-named modules are ``psf.py`` (Synth
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from typing import List, Sequence, Union
 
@@ -224,16 +226,34 @@ def generate_all(fs: Sequence[MLPBlock], g: MLPBlock, data: torch.Tensor, interl
 
 
 class _SkinnyLinear(torch.autograd.Function):
-    """``x @ W^T + b`` for a very narrow input (init_linear = Linear(2, E), psf.py:136-141) over millions of rows.
-    Forward is addmm; the weight gradient ``dy^T x`` (E x 2 output, K = B*n) is evaluated split-K as a batched GEMM —
-    autograd's single GEMM picks a 128x32 SIMT tile for it (0.8 ms of a 16 ms step at cfg2)."""
+    """``x @ W^T + b`` for a very narrow input (init_linear = Linear(2, E), psf.py:136-141) over millions of rows: one
+    streaming kernel each way (csrc/psf_embed.cu: a 277 MB write forward, one pass over dy for dW and db backward).  The
+    library route - addmm forward, split-K batched GEMM and two column reductions backward - took 0.46 ms of the 8.4 ms
+    step at cfg2.  Shapes outside the kernels (out_features not a multiple of 4, > 128) keep that route."""
 
     KC = 4096
 
     @staticmethod
+    def _native(x2d, w):
+        E, IN = w.shape
+        return (os.environ.get("PSF_INIT_LINEAR_KERNELS", "1") != "0" and x2d.dtype == torch.float32 and w.dtype == torch.float32 and IN <= 4 and E % 4 == 0 and E <= 128
+                and 256 % (E // 4) == 0 and x2d.shape[0] > 0)
+
+    @staticmethod
     def forward(ctx, x2d, w, b):
+        x2d = x2d.contiguous()
         ctx.save_for_backward(x2d, w)
-        return torch.addmm(b, x2d, w.t())
+        ctx.native = _SkinnyLinear._native(x2d, w)
+        if not ctx.native:
+            return torch.addmm(b, x2d, w.t())
+        lib = _capi.load()
+        wc, bc = w.contiguous(), b.contiguous()
+        y = torch.empty(x2d.shape[0], w.shape[0], dtype=torch.float32, device=x2d.device)
+        with torch.cuda.device(x2d.device):
+            rc = lib.psf_init_linear_fwd(x2d.data_ptr(), wc.data_ptr(), bc.data_ptr(), y.data_ptr(), x2d.shape[0], w.shape[1],
+                                         w.shape[0], torch.cuda.current_stream().cuda_stream)
+        _capi.check(rc, "psf_init_linear_fwd")
+        return y
 
     @staticmethod
     @torch.autograd.function.once_differentiable
@@ -242,6 +262,16 @@ class _SkinnyLinear(torch.autograd.Function):
         dy = dy.contiguous()
         rows = x2d.shape[0]
         dx = dy @ w if ctx.needs_input_grad[0] else None
+        if ctx.native:
+            lib = _capi.load()
+            dw, db = torch.empty_like(w, memory_format=torch.contiguous_format), torch.empty(w.shape[0], dtype=w.dtype, device=w.device)
+            with torch.cuda.device(x2d.device):
+                nbytes = int(lib.psf_init_linear_workspace_bytes(rows, w.shape[1], w.shape[0]))
+                ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=x2d.device)
+                rc = lib.psf_init_linear_bwd(x2d.data_ptr(), dy.data_ptr(), dw.data_ptr(), db.data_ptr(), rows, w.shape[1],
+                                             w.shape[0], ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+            _capi.check(rc, "psf_init_linear_bwd")
+            return dx, dw, db
         kc = min(_SkinnyLinear.KC, rows)
         S, main = rows // kc, (rows // kc) * kc                                            # full chunks + remainder
         part = torch.bmm(dy[:main].view(S, kc, -1).transpose(1, 2), x2d[:main].reshape(S, kc, -1))   # [S, E, in]

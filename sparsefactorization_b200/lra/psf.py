@@ -5,6 +5,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
+from ..head import apply_head
 from .._psfnet import MakeMLP, MLPBlock, PSFChainMixin, get_chord_indices_assym  # noqa: F401
 
 __all__ = ["get_chord_indices_assym", "MakeMLP", "MLPBlock", "PSFNet"]
@@ -106,7 +107,7 @@ class PSFNet(PSFChainMixin, nn.Module):
         V = self.dropout3(V)
         if self.pooling_type == 'CLS':
             V = V[:, 0, :]
-        return self.final(V.reshape(V.size(0), -1))
+        return apply_head(self.final, V.reshape(V.size(0), -1))
 
     def forward_with_attention_map(self, data):
         """``(logits, W_final)`` like ``ChangedPSF.forward`` of the reference's attention-map scripts
@@ -117,4 +118,4 @@ class PSFNet(PSFChainMixin, nn.Module):
         V = self.dropout3(V)
         if self.pooling_type == 'CLS':
             V = V[:, 0, :]
-        return self.final(V.reshape(V.size(0), -1)), self.attention_map(emb)
+        return apply_head(self.final, V.reshape(V.size(0), -1)), self.attention_map(emb)

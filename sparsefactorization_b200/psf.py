@@ -10,6 +10,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
+from .head import apply_head
 from ._psfnet import (MakeMLP, MLPBlock, PSFChainMixin, chord_mask, get_chord_indices_assym,  # noqa: F401
                       skinny_linear)
 
@@ -77,4 +78,4 @@ class PSFNet(PSFChainMixin, nn.Module):
             positions = perm if perm is not None else torch.arange(0, self.n_vec, device=data.device)
             data = data + self.pos_embedding(positions.expand(data.size(0), self.n_vec))
         V = self._chain_from_data(data, pre_interleaved=Q)   # V = g(data), all n_W factors (+ residual V_0 after each)
-        return self.final(V.reshape(V.size(0), -1))
+        return apply_head(self.final, V.reshape(V.size(0), -1))
