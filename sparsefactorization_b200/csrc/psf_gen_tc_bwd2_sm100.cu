@@ -37,7 +37,7 @@
 //                [dpre | hid] (hi, lo) -> shared memory B operand, dout of step s + 2 -> tensor memory A operand of
 //                dhid
 //   warps 16-19  helpers, one per 32-lane quarter: x -> tensor memory, dx writer, D drain (red.global into the CTA's slice);
-//                warps 16 / 18 build x^T, warps 17 / 19 the dout^T strips of even / odd steps (+ db2)
+//                warps 16 / 18 build x^T and sum dout over the rows (db2), warps 17 / 19 the dout^T strips of even / odd steps
 //   warp 20      tensor-memory allocation + the thread issuing the row-local MMAs;  warp 23  the thread issuing the
 //                gradient MMAs
 //   warp 21      TMA: weight images (3 stages);  warp 22  TMA: dout staging tiles (4 stages)
@@ -156,7 +156,8 @@ __global__ void __launch_bounds__(kThreads2, 1) psf_gen_bwd_tc2_kernel(const Gen
     }
     for (int i = 0; i < kDsStages; ++i) {
       mbar_init(bar(Q_DSFULL0 + i), 1);           // TMA thread (+ bytes)
-      mbar_init(bar(Q_DSFREE0 + i), kEpi + 1);    // the epilogue warps (dout -> tensor memory) and the step's strip builder
+      mbar_init(bar(Q_DSFREE0 + i), kEpi + 2);    // the epilogue warps (dout -> tensor memory), the step's strip builder and
+                                                  // the x^T warp that sums its columns (db2)
     }
     for (int i = 0; i < kWStages; ++i) {
       mbar_init(bar(Q_WFULL0 + i), 1);
@@ -387,12 +388,10 @@ __global__ void __launch_bounds__(kThreads2, 1) psf_gen_bwd_tc2_kernel(const Gen
     // tap lane 15 a row of ones - and db2.  The caller has seen the gradient product of step t - 2 finish.
     auto build_strip = [&](uint32_t t, uint32_t m) {       // m = generator of step t
       const uint32_t b = t % kDsStages;
-      const int Lm = m < (uint32_t)p.n_W ? p.L : p.C;
       const float* ds = reinterpret_cast<const float*>(smem + kOffDs + b * kDsBuf);
       TL(10, t);
       mbar_wait_tc(bar(Q_DSFULL0 + b), (t / kDsStages) & 1);
       TL(11, t);
-      float sum = 0.f;
       if (m < (uint32_t)p.n_W) {
         // staged tap-major [tap][row]; taps >= L hold stale finite values (their D rows are never read) and tap row 15 of
         // every staging tile holds ones (written at kernel start, out of reach of the copies)
@@ -406,7 +405,6 @@ __global__ void __launch_bounds__(kThreads2, 1) psf_gen_bwd_tc2_kernel(const Gen
             const float e[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              sum += e[j];
               const float h = tf32_hi(e[j]);
               o[4 * i + j] = is_lo ? e[j] - h : h;
             }
@@ -424,7 +422,6 @@ __global__ void __launch_bounds__(kThreads2, 1) psf_gen_bwd_tc2_kernel(const Gen
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
             const float v = dv[(32 * c + k) * stride];
-            sum += v;
             const float h = tf32_hi(v);
             o[k] = is_lo ? v - h : h;
           }
@@ -433,19 +430,45 @@ __global__ void __launch_bounds__(kThreads2, 1) psf_gen_bwd_tc2_kernel(const Gen
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(Q_DSFREE0 + b));
-      if (lane < Lm) red1(wsc + (long long)m * kAccBlk + GH * GE + GH + GLP * GH + lane, sum);      // db2
       tmem_wait_st_tc();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(Q_ATDFULL0 + par_mine));
       TL(12, t);
     };
+    // warps 16 / 18 (which have slack; the strip warps are the critical ones): db2 = column sums of dout of the even / odd
+    // steps, straight from the staging tile (lane = tap; the upper half warp idles)
+    auto sum_dout = [&](uint32_t t, uint32_t m) {
+      const uint32_t b = t % kDsStages;
+      const int Lm = m < (uint32_t)p.n_W ? p.L : p.C;
+      const float* ds = reinterpret_cast<const float*>(smem + kOffDs + b * kDsBuf);
+      mbar_wait_tc(bar(Q_DSFULL0 + b), (t / kDsStages) & 1);
+      float sum = 0.f;
+      if (lane < Lm) {
+        if (m < (uint32_t)p.n_W) {
+          const float4* dr = reinterpret_cast<const float4*>(ds + lane * kDsRow);
+#pragma unroll 8
+          for (int i = 0; i < 32; ++i) {
+            const float4 q = dr[i];
+            sum += (q.x + q.y) + (q.z + q.w);
+          }
+        } else {
+#pragma unroll 8
+          for (int r = 0; r < 128; ++r) sum += ds[r * p.C + lane];
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(Q_DSFREE0 + b));
+      if (lane < Lm) red1(wsc + (long long)m * kAccBlk + GH * GE + GH + GLP * GH + lane, sum);
+    };
+    const uint32_t par_x = (uint32_t)(quarter >> 1);        // warp 16: even steps, warp 18: odd steps
     if (my_tiles > 0) {
       prepare_x(0);
       if (xside) build_xT(0);
       else if (par_mine < total) build_strip(par_mine, par_mine % (uint32_t)n_gen);
       for (uint32_t t = 1; t <= 2; ++t)                   // tiles whose first products are issued ahead of the loop
         if (t < total && t % (uint32_t)n_gen == 0) prepare_x(t / (uint32_t)n_gen);
+      if (xside && par_x < total) sum_dout(par_x, par_x % (uint32_t)n_gen);
     }
     uint32_t m = 0, it = 0;                                // generator and tile of step s (no divisions in the loop:
     uint32_t m2h = 2 % (uint32_t)n_gen;                    // every instruction of a helper costs ~10 cycles), and the
@@ -503,6 +526,7 @@ __global__ void __launch_bounds__(kThreads2, 1) psf_gen_bwd_tc2_kernel(const Gen
         TL(15, s);
         if (strip && s + 2 < total) build_strip(s + 2, m2h);
         if (xside && last && it + 1 < (uint32_t)my_tiles) build_xT(it + 1);
+        if (xside && par_x == par && s + 2 < total) sum_dout(s + 2, m2h);
       }
       // x of the next tile, three steps before its first products are issued (n_gen >= 3; shorter chains: see the prologue)
       if (s + 3 < total && (n_gen >= 3 ? m + 3 == (uint32_t)n_gen : (s + 3) % (uint32_t)n_gen == 0))
