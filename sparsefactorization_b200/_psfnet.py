@@ -232,6 +232,7 @@ class _SkinnyLinear(torch.autograd.Function):
     step at cfg2.  Shapes outside the kernels (out_features not a multiple of 4, > 128) keep that route."""
 
     KC = 4096
+    launches = 0      # kernels of libpsf_b200.so launched (bench.py's gpu_launches)
 
     @staticmethod
     def _native(x2d, w):
@@ -253,6 +254,7 @@ class _SkinnyLinear(torch.autograd.Function):
             rc = lib.psf_init_linear_fwd(x2d.data_ptr(), wc.data_ptr(), bc.data_ptr(), y.data_ptr(), x2d.shape[0], w.shape[1],
                                          w.shape[0], torch.cuda.current_stream().cuda_stream)
         _capi.check(rc, "psf_init_linear_fwd")
+        _SkinnyLinear.launches += 1
         return y
 
     @staticmethod
@@ -271,6 +273,7 @@ class _SkinnyLinear(torch.autograd.Function):
                 rc = lib.psf_init_linear_bwd(x2d.data_ptr(), dy.data_ptr(), dw.data_ptr(), db.data_ptr(), rows, w.shape[1],
                                              w.shape[0], ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
             _capi.check(rc, "psf_init_linear_bwd")
+            _SkinnyLinear.launches += 2            # the pass over dy + the reduction of the CTA partials
             return dx, dw, db
         kc = min(_SkinnyLinear.KC, rows)
         S, main = rows // kc, (rows // kc) * kc                                            # full chunks + remainder

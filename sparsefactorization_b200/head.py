@@ -16,6 +16,7 @@ from torch import nn
 from . import _capi
 
 MAX_CLASSES = 16
+launches = 0          # kernels of libpsf_b200.so launched through this module (bench.py's gpu_launches)
 
 
 class _FlatHead(torch.autograd.Function):
@@ -31,6 +32,8 @@ class _FlatHead(torch.autograd.Function):
             rc = lib.psf_head_fwd(V2d.data_ptr(), weight.data_ptr(), bias.data_ptr() if bias is not None else None,
                                   out.data_ptr(), B, K, nc, ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
         _capi.check(rc, "psf_head_fwd")
+        global launches
+        launches += 2                              # chunk sums + their reduction
         ctx.save_for_backward(V2d, weight)
         ctx.has_bias = bias is not None
         return out
@@ -50,6 +53,8 @@ class _FlatHead(torch.autograd.Function):
             rc = lib.psf_head_bwd(V2d.data_ptr(), weight.data_ptr(), g.data_ptr(), dV.data_ptr(), dW.data_ptr(), B, K, nc,
                                   ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
         _capi.check(rc, "psf_head_bwd")
+        global launches
+        launches += 2 if B >= 8 else 1             # fused dV / dW pass (+ the reduction over the batch slices)
         return dV, dW, (g.sum(0) if ctx.has_bias else None)
 
 
