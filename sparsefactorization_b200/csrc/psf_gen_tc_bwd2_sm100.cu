@@ -125,6 +125,30 @@ __device__ __forceinline__ void normal_cdf_pdf2(float p, float& cdf, float& pdf)
   pdf = 0.39894228f * e;
 }
 
+// the same on two values with packed arithmetic (same operations in the same order per value)
+__device__ __forceinline__ void normal_cdf_pdf2x2(uint64_t p2, uint64_t& cdf2, uint64_t& pdf2) {
+  float pa, pb;
+  unpack2f(p2, pa, pb);
+  const uint64_t ax2 = pack2f(fabsf(pa), fabsf(pb));
+  float ua, ub;
+  unpack2f(fma2f(ax2, dup2f(0.27599917f), dup2f(1.f)), ua, ub);
+  const uint64_t t2 = pack2f(rcp_approx(ua), rcp_approx(ub));
+  uint64_t q2 = fma2f(dup2f(-0.22690525f), t2, dup2f(0.88164259f));
+  q2 = fma2f(q2, t2, dup2f(-0.62774200f));
+  q2 = fma2f(q2, t2, dup2f(0.64431879f));
+  q2 = fma2f(q2, t2, dup2f(0.093436931f));
+  q2 = fma2f(q2, t2, dup2f(0.23524893f));
+  float ea, eb;
+  unpack2f(mul2f(mul2f(p2, p2), dup2f(-0.72134752f)), ea, eb);
+  const uint64_t e2 = pack2f(ex2_approx(ea), ex2_approx(eb));
+  const uint64_t tail2 = mul2f(mul2f(dup2f(0.5f), mul2f(q2, t2)), e2);
+  float ta, tb, oa, ob;
+  unpack2f(tail2, ta, tb);
+  unpack2f(fma2f(tail2, dup2f(-1.f), dup2f(1.f)), oa, ob);
+  cdf2 = pack2f(pa >= 0.f ? oa : ta, pb >= 0.f ? ob : tb);
+  pdf2 = mul2f(dup2f(0.39894228f), e2);
+}
+
 __global__ void __launch_bounds__(kThreads2, 1) psf_gen_bwd_tc2_kernel(const GenParams p, const uint8_t* __restrict__ img) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -250,21 +274,20 @@ __global__ void __launch_bounds__(kThreads2, 1) psf_gen_bwd_tc2_kernel(const Gen
       tmem_ld8f(tb + cDhid + 8 * cq, dh);
       tmem_wait_ld_tc();
       const float* b1 = reinterpret_cast<const float*>(smem + kOffW + wst * kImg + kB1) + 8 * cq;
-#pragma unroll
-      for (int h = 0; h < 8; ++h) {
-        const float pv = tc_unbias(pre[h]) + b1[h];
-        float cdf, pdf;
-        normal_cdf_pdf2(pv, cdf, pdf);
-        pre[h] = dh[h] * fmaf(pv, pdf, cdf);               // dpre
-        dh[h] = pv * cdf;                                  // hid
-      }
       float ph[8], hh[8];
 #pragma unroll
-      for (int h = 0; h < 8; ++h) {
-        ph[h] = tf32_hi(pre[h]);
-        pre[h] -= ph[h];                                   // dpre lo
-        hh[h] = tf32_hi(dh[h]);
-        dh[h] -= hh[h];                                    // hid lo
+      for (int h = 0; h < 8; h += 2) {                     // two hidden units at a time, packed arithmetic
+        const uint64_t pv2 = fma2f(pack2f(tc_unbias(pre[h]), tc_unbias(pre[h + 1])), dup2f(1.f), pack2f(b1[h], b1[h + 1]));
+        uint64_t cdf2, pdf2, hi, lo;
+        normal_cdf_pdf2x2(pv2, cdf2, pdf2);
+        const uint64_t dpre2 = mul2f(pack2f(dh[h], dh[h + 1]), fma2f(pv2, pdf2, cdf2));
+        const uint64_t hid2 = mul2f(pv2, cdf2);
+        tf32_split2(dpre2, hi, lo);
+        unpack2f(hi, ph[h], ph[h + 1]);
+        unpack2f(lo, pre[h], pre[h + 1]);                  // dpre lo
+        tf32_split2(hid2, hi, lo);
+        unpack2f(hi, hh[h], hh[h + 1]);
+        unpack2f(lo, dh[h], dh[h + 1]);                    // hid lo
       }
       // [dpre | hid] (hi, lo) -> the B operand of the gradient product; the buffer is free once the product of step s - 2
       // is done

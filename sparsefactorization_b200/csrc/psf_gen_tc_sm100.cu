@@ -64,6 +64,27 @@ __device__ __forceinline__ float gelu_erf(float v) {
   return fmaxf(v, 0.f) - s;
 }
 
+// The same on two values with packed arithmetic (same operations in the same order per value: bit-identical results):
+// 2 x (abs, max, 2 MUFU) + 15 packed instructions per pair instead of 2 x 15.
+__device__ __forceinline__ uint64_t gelu_erf2(uint64_t v2) {
+  float va, vb;
+  unpack2f(v2, va, vb);
+  const uint64_t ax2 = pack2f(fabsf(va), fabsf(vb));
+  float ua, ub;
+  unpack2f(fma2f(ax2, dup2f(0.27599917f), dup2f(1.f)), ua, ub);
+  const uint64_t t2 = pack2f(rcp_approx(ua), rcp_approx(ub));
+  uint64_t q2 = fma2f(dup2f(-0.22690525f), t2, dup2f(0.88164259f));
+  q2 = fma2f(q2, t2, dup2f(-0.62774200f));
+  q2 = fma2f(q2, t2, dup2f(0.64431879f));
+  q2 = fma2f(q2, t2, dup2f(0.093436931f));
+  q2 = fma2f(q2, t2, dup2f(0.23524893f));
+  float ea, eb;
+  unpack2f(mul2f(mul2f(v2, v2), dup2f(-0.72134752f)), ea, eb);
+  const uint64_t e2 = pack2f(ex2_approx(ea), ex2_approx(eb));
+  const uint64_t s2 = mul2f(mul2f(mul2f(dup2f(0.5f), ax2), mul2f(q2, t2)), e2);
+  return fma2f(s2, dup2f(-1.f), pack2f(fmaxf(va, 0.f), fmaxf(vb, 0.f)));
+}
+
 __global__ void __launch_bounds__(kThreadsTC, 1) psf_gen_fwd_tc_kernel(const GenParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -182,12 +203,19 @@ __global__ void __launch_bounds__(kThreadsTC, 1) psf_gen_fwd_tc_kernel(const Gen
           }
           const float* b1 = b1s + m * GH;
 #pragma unroll
+          float vh[32];                                    // hidden units: (hi, lo) for the layer-2 A operand
           for (int h4 = 0; h4 < GH / 4; ++h4) {
             const float4 b = *reinterpret_cast<const float4*>(b1 + 4 * h4);
-            v[4 * h4 + 0] = gelu_erf(tc_unbias(v[4 * h4 + 0]) + b.x);
-            v[4 * h4 + 1] = gelu_erf(tc_unbias(v[4 * h4 + 1]) + b.y);
-            v[4 * h4 + 2] = gelu_erf(tc_unbias(v[4 * h4 + 2]) + b.z);
-            v[4 * h4 + 3] = gelu_erf(tc_unbias(v[4 * h4 + 3]) + b.w);
+            const uint64_t one = dup2f(1.f);
+            const uint64_t g0 = gelu_erf2(fma2f(pack2f(tc_unbias(v[4 * h4 + 0]), tc_unbias(v[4 * h4 + 1])), one, pack2f(b.x, b.y)));
+            const uint64_t g1 = gelu_erf2(fma2f(pack2f(tc_unbias(v[4 * h4 + 2]), tc_unbias(v[4 * h4 + 3])), one, pack2f(b.z, b.w)));
+            uint64_t hi, lo;
+            tf32_split2(g0, hi, lo);
+            unpack2f(hi, vh[4 * h4 + 0], vh[4 * h4 + 1]);
+            unpack2f(lo, v[4 * h4 + 0], v[4 * h4 + 1]);
+            tf32_split2(g1, hi, lo);
+            unpack2f(hi, vh[4 * h4 + 2], vh[4 * h4 + 3]);
+            unpack2f(lo, v[4 * h4 + 2], v[4 * h4 + 3]);
           }
           float o[16];
           if (pending) {     // the previous generator's layer 2 has finished: its result out, the hid columns free
@@ -196,15 +224,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) psf_gen_fwd_tc_kernel(const Gen
             tmem_ld16f(t_out, o);
             tmem_wait_ld_tc();
           }
-          {
-            float vh[32];
-#pragma unroll
-            for (int h = 0; h < GH; ++h) vh[h] = tf32_hi(v[h]);
-            tmem_st32f(t_hid, vh);
-#pragma unroll
-            for (int h = 0; h < GH; ++h) v[h] -= vh[h];
-            tmem_st32f(t_hid + 32, v);
-          }
+          tmem_st32f(t_hid, vh);
+          tmem_st32f(t_hid + 32, v);
           tmem_wait_st_tc();
           tc_fence_before();
           __syncwarp();

@@ -133,6 +133,34 @@ __device__ __forceinline__ void tmem_ld8f(uint32_t taddr, float (&v)[8]) {
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
 __device__ __forceinline__ float tf32_lo(float v) { return v - tf32_hi(v); }
 
+// Packed FP32 pairs (FMUL2 / FFMA2 on sm_100: one issue slot for two values).  The epilogue warps of the generator
+// kernels are bound by issue slots, and their per-element arithmetic is the same polynomial with the same constants.
+__device__ __forceinline__ uint64_t pack2f(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2f(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t mul2f(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fma2f(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t dup2f(float a) { return pack2f(a, a); }
+// Veltkamp's form of the tf32 split on a pair: t = (2^13 + 1) v, hi = t - (t - v) is v rounded to nearest with 11
+// significant bits - exactly a tf32 - and lo = v - hi is exact; four packed instructions for (hi, lo) of two values
+__device__ __forceinline__ void tf32_split2(uint64_t v, uint64_t& hi, uint64_t& lo) {
+  const uint64_t m1 = dup2f(-1.f);
+  const uint64_t t = mul2f(v, dup2f(8193.f));
+  hi = fma2f(fma2f(v, m1, t), m1, t);                   // t - (t - v)
+  lo = fma2f(hi, m1, v);
+}
+
 // The tensor core adds into its fp32 accumulator by truncation (measured: tools/microbench/umma_probe.cu,
 // tools/gen_bias_check.py), so a K = 32 product - four full-magnitude accumulations after the small 3xTF32 terms - comes
 // out biased towards zero, where round-to-nearest FMA chains are unbiased: every W shrinks by 1.5e-7 on average (1.7 ulp),
