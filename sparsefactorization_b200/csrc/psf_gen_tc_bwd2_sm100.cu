@@ -576,9 +576,9 @@ __global__ void __launch_bounds__(kThreads2, 1) psf_gen_bwd_tc2_kernel(const Gen
       // pre = x W1^T and dhid = dout W2 of step t into the (pre, dhid) set t & 1
       auto issue_pd = [&](uint32_t t, const Ctr& c) {
         const uint32_t cPre = tmem + cPD + 64 * (t & 1), cDhid = cPre + 32;
-        if (c.m == 0) mbar_wait_tc(bar(Q_XFULL), c.it & 1);
+        if (c.m == 0) mbar_wait_hot(bar(Q_XFULL), c.it & 1);
         TL(30, t);
-        mbar_wait_tc(bar(Q_WFULL0 + c.st), c.wph);
+        mbar_wait_hot(bar(Q_WFULL0 + c.st), c.wph);
         TL(31, t);
         tc_fence_after();
         const uint32_t w = w0 + c.st * (kImg >> 4);
@@ -598,17 +598,17 @@ __global__ void __launch_bounds__(kThreads2, 1) psf_gen_bwd_tc2_kernel(const Gen
         if (c.m == (uint32_t)n_gen - 1) mma_commit(bar(Q_XEMPTY));
       };
       Ctr cs = {0, 0, 0, 0}, ct = {0, 0, 0, 0};              // step s (dx) and step t = s + 2 (row-local products)
-      if (total > 0) mbar_wait_tc(bar(Q_DOUTT), 0), issue_pd(0, ct), advance(ct);
-      if (total > 1) mbar_wait_tc(bar(Q_DOUTT), 1), issue_pd(1, ct), advance(ct);
+      if (total > 0) mbar_wait_hot(bar(Q_DOUTT), 0), issue_pd(0, ct), advance(ct);
+      if (total > 1) mbar_wait_hot(bar(Q_DOUTT), 1), issue_pd(1, ct), advance(ct);
       for (uint32_t s = 0; s < total; ++s) {
         const uint32_t par = s & 1;
         const uint32_t cPre = tmem + cPD + 64 * par, cDhid = cPre + 32;
         const bool last = cs.m == (uint32_t)n_gen - 1;
         // ---- dx += dpre W1 (A = dpre, which the epilogue wrote over pre / dhid; the arrival also covers dout(s + 2)) ----
         TL(20, s);
-        mbar_wait_tc(bar(Q_DPREFULL0 + par), (s >> 1) & 1);
+        mbar_wait_hot(bar(Q_DPREFULL0 + par), (s >> 1) & 1);
         TL(21, s);
-        if (cs.m == 0) mbar_wait_tc(bar(Q_DXEMPTY), (cs.it & 1) ^ 1);
+        if (cs.m == 0) mbar_wait_hot(bar(Q_DXEMPTY), (cs.it & 1) ^ 1);
         tc_fence_after();
         {
           const uint32_t w = w0 + cs.st * (kImg >> 4);
@@ -643,11 +643,11 @@ __global__ void __launch_bounds__(kThreads2, 1) psf_gen_bwd_tc2_kernel(const Gen
       for (uint32_t s = 0; s < total; ++s) {
         const uint32_t par = s & 1, ph = (s >> 1) & 1;
         // ---- D = A_T . [dpre | hid]  (K = the tile's 128 rows; B_lo first) ----
-        mbar_wait_tc(bar(Q_DPREFULL0 + par), ph);           // B of step s
-        mbar_wait_tc(bar(Q_ATDFULL0 + par), ph);
+        mbar_wait_hot(bar(Q_DPREFULL0 + par), ph);           // B of step s
+        mbar_wait_hot(bar(Q_ATDFULL0 + par), ph);
         TL(26, s);
-        if (m == 0) mbar_wait_tc(bar(Q_ATXFULL), it & 1);
-        mbar_wait_tc(bar(Q_DFREE0 + par), ph ^ 1);
+        if (m == 0) mbar_wait_hot(bar(Q_ATXFULL), it & 1);
+        mbar_wait_hot(bar(Q_DFREE0 + par), ph ^ 1);
         TL(24, s);
         tc_fence_after();
         {

@@ -295,8 +295,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) psf_gen_fwd_tc_kernel(const Gen
       const uint32_t Q = (uint32_t)(my_tiles * nch);
       auto issue_pre = [&](uint32_t q) {
         const uint32_t c = q % (uint32_t)nch, it = q / (uint32_t)nch, stage = q & 1;
-        if (c == 0) mbar_wait_tc(bars + 8 * BAR_XFULL, it & 1);
-        mbar_wait_tc(bars + 8 * (BAR_PREEMPTY0 + stage), ((q >> 1) & 1) ^ 1);
+        if (c == 0) mbar_wait_hot(bars + 8 * BAR_XFULL, it & 1);
+        mbar_wait_hot(bars + 8 * (BAR_PREEMPTY0 + stage), ((q >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d = tmem + kColPre + stage * 128;
         const uint32_t w1 = sbase + c * kW1Chunk;
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) psf_gen_fwd_tc_kernel(const Gen
           const int m = (int)c * 4 + j;
           if (m >= n_gen) break;
           const int wg = j & 1;
-          mbar_wait_tc(bars + 8 * (BAR_HIDFULL0 + wg), (wg ? k1 : k0) & 1);
+          mbar_wait_hot(bars + 8 * (BAR_HIDFULL0 + wg), (wg ? k1 : k0) & 1);
           if (wg) ++k1; else ++k0;
           tc_fence_after();
           const uint32_t d = tmem + kColOut + 16 * wg;

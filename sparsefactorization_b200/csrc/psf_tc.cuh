@@ -35,6 +35,17 @@ __device__ __forceinline__ void mbar_wait_tc(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// same for the lone MMA-issuing threads: one lane polling costs next to nothing in issue slots, and every cycle it
+// sleeps past an arrival is added to a hop of the pipeline
+__device__ __forceinline__ void mbar_wait_hot(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try(bar, parity)) {
+    if (++spins > PSF_TC_SPINS) {
+      PSF_TC_TIMEOUT(bar, parity);
+      PSF_TC_GIVE_UP;
+    }
+  }
+}
 // same for warps with slack (loaders)
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
