@@ -735,7 +735,9 @@ extern "C" int psf_debug_timeline(unsigned* out) {     // out: 24 warps x kTlPer
 // Shapes the kernel covers: whole 128-row tiles, tap-major dW with 16-byte aligned 512-byte runs per tap.
 int psf_gen_tc_bwd2(const GenParams& p, const void* images, int* grid_out, cudaStream_t st) {
   // tap lane 15 of the dout^T strips is the row of ones that yields db1
-  if (p.n_gen < 1 || p.L > GLP - 1 || p.C > GLP - 1 || p.pre != nullptr) return PSF_ERR_UNSUPPORTED;
+  // (chains of fewer than three generators take the first-version kernel: the look-ahead of this one - products two steps
+  // ahead, x three steps ahead - is only exercised by the tests from three generators per tile on)
+  if (p.n_gen < 3 || p.L > GLP - 1 || p.C > GLP - 1 || p.pre != nullptr) return PSF_ERR_UNSUPPORTED;
   if ((p.rows & 127) || (p.sWt & 3) || (p.sWf & 3) || (reinterpret_cast<uintptr_t>(p.Wt) & 15)) return PSF_ERR_UNSUPPORTED;
   if (p.n_gen > p.n_W && (reinterpret_cast<uintptr_t>(p.V) & 15)) return PSF_ERR_UNSUPPORTED;      // dV0 tiles go through TMA
   if (reinterpret_cast<uintptr_t>(images) & 127) return PSF_ERR_UNSUPPORTED;

@@ -118,3 +118,19 @@ def test_synthetic_data_shapes_and_labels():
     assert torch.equal(Y, 2 * (vals[:, 0] == 5).long() + (vals[:, 1] == 5).long())
     X, Y = data.listops_shaped(8, 100, vocab_size=17)
     assert X.shape == (8, 100) and torch.all(X[:, 0] == 16) and int(X.max()) == 16 and int(Y.max()) <= 9
+
+
+def test_small_operator_wrappers_keep_linear_off_the_gpu():
+    """head.flat_linear / _psfnet.skinny_linear only take the CUDA kernels for CUDA fp32 tensors."""
+    from torch import nn
+    from sparsefactorization_b200 import head
+    from sparsefactorization_b200._psfnet import skinny_linear
+    lin = nn.Linear(8192, 2)
+    V = torch.randn(3, 8192)
+    assert not head.covers(lin, V)
+    torch.testing.assert_close(head.apply_head(lin, V), lin(V))
+    seq = nn.Sequential(nn.Linear(8192, 16), nn.GELU(), nn.Linear(16, 4))
+    torch.testing.assert_close(head.apply_head(seq, V), seq(V))
+    init = nn.Linear(2, 32)
+    x = torch.randn(2, 64, 2)
+    torch.testing.assert_close(skinny_linear(init, x), init(x))
