@@ -1,0 +1,2 @@
+"""LRA/psf.py by name."""
+from sparsefactorization_b200.lra.psf import PSFNet, MakeMLP, MLPBlock, get_chord_indices_assym  # noqa: F401
