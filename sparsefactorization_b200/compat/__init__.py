@@ -2,12 +2,12 @@
 ``synthetic_training_config`` ...), one per reference folder, so that its scripts run unchanged with the directory first on
 ``sys.path``::
 
-    PYTHONPATH=$(python -m sparsefactorization_b200.compat synthetic) python -P psf_training.py      # SyntheticExperiments/
-    PYTHONPATH=$(python -m sparsefactorization_b200.compat lra) python -P listops_training.py        # LRA/
-    PYTHONPATH=$(python -m sparsefactorization_b200.compat genome) python -P genome_clf_training.py  # Genome_Clf/
-    PYTHONPATH=$(python -m sparsefactorization_b200.compat spmul) python -P sf_parametric_cuda.py    # spmul/
+    PYTHONPATH=$(python -m sparsefactorization_b200.compat synthetic):$REPO python -P psf_training.py      # SyntheticExperiments/
+    PYTHONPATH=$(python -m sparsefactorization_b200.compat lra):$REPO python -P listops_training.py        # LRA/
+    PYTHONPATH=$(python -m sparsefactorization_b200.compat genome):$REPO python -P genome_clf_training.py  # Genome_Clf/
+    PYTHONPATH=$(python -m sparsefactorization_b200.compat spmul):$REPO python -P sf_parametric_cuda.py    # spmul/
 
-(``-P``, Python >= 3.11: do not put the script's own directory - which holds the reference's ``psf.py`` - first.)
+(``$REPO``: the root of this repository, so that the package itself is importable.  ``-P``, Python >= 3.11: do not put the script's own directory - which holds the reference's ``psf.py`` - first.)
 Each file is a one-line re-export of the module documented in INTEGRATION.md section 1.
 """
 import os
