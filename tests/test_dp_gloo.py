@@ -134,3 +134,41 @@ def test_dataset_creator_label_dtypes():
     assert lra_utils.DatasetCreator(data, torch.arange(4, dtype=torch.int32))[0][1].dtype == torch.long
     assert genome_utils.DatasetCreator(data, torch.arange(4, dtype=torch.int16))[0][1].dtype == torch.long
     assert len(lra_utils.DatasetCreator(data, torch.arange(4))) == 4
+
+
+def _clip_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(3)
+        X, Y = 50.0 * torch.randn(8, 6, generator=g), 50.0 * torch.randn(8, generator=g)      # large gradients
+        net = _make_net()
+        wrap = dp.DataParallel(net)
+        wrap.broadcast_parameters()
+        lo, hi = dp.shard_range(8)
+        opt = torch.optim.SGD(net.parameters(), lr=0.0)
+        dp.train_step(net, wrap, opt, torch.nn.MSELoss(), X[lo:hi], Y[lo:hi], clip_grad_norm=1.0)
+        grads = torch.cat([p.grad.reshape(-1) for p in net.parameters() if p.grad is not None])
+        hist = dp.TrainModelDP(_make_net(), (X, Y), (X, Y), (X, Y), n_epochs=1, test_freq=1,
+                               optimizer=torch.optim.SGD(net.parameters(), lr=0.0), loss=torch.nn.MSELoss(), problem="adding",
+                               saving_criteria=1e9, batch_size=2, verbose=False, clip_grad_norm=1.0)
+        q.put((rank, float(grads.norm()), grads.tolist(), len(hist)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_clip_grad_norm_applies_after_the_all_reduce():
+    """Genome loop (Genome_Clf/psf_utils.py:73): the clip sees the averaged gradient, identically on every rank."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_clip_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    (_, n0, g0, h0), (_, n1, g1, h1) = res
+    assert abs(n0 - 1.0) < 1e-4 and abs(n1 - 1.0) < 1e-4          # clipped to the max norm
+    assert g0 == g1 and h0 == h1 == 1
