@@ -86,17 +86,27 @@ __global__ void __launch_bounds__(kEmbThreads) psf_embed_bwd_kernel(const float*
   }
 }
 
-// dW[e][i], db[e] = sums of the CTA partials, in CTA order
-__global__ void psf_embed_bwd_reduce_kernel(const float* __restrict__ part, float* __restrict__ dW, float* __restrict__ db, int ctas,
-                                            int E, int IN) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int per = E * (IN + 1);
-  if (t >= per) return;
+// dW[e][i], db[e] = sums of the CTA partials: one block per output element, strided partial sums per thread and a fixed
+// tree over the block, in double (a single thread walking the ~1200 partials took 117 us: a chain of L2 latencies)
+constexpr int kEmbRedThreads = 128;
+__global__ void __launch_bounds__(kEmbRedThreads) psf_embed_bwd_reduce_kernel(const float* __restrict__ part, float* __restrict__ dW,
+                                                                               float* __restrict__ db, int ctas, int E, int IN) {
+  __shared__ double sh[kEmbRedThreads];
+  const int t = blockIdx.x, per = E * (IN + 1);
   double s = 0.0;
-  for (int c = 0; c < ctas; ++c) s += (double)part[(long long)c * per + t];
-  const int e = t / (IN + 1), i = t - e * (IN + 1);
-  if (i < IN) dW[e * IN + i] = (float)s;
-  else if (db) db[e] = (float)s;
+  for (int c = threadIdx.x; c < ctas; c += kEmbRedThreads) s += (double)part[(long long)c * per + t];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+#pragma unroll
+  for (int o = kEmbRedThreads / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const int e = t / (IN + 1), i = t - e * (IN + 1);
+    if (i < IN) dW[e * IN + i] = (float)sh[0];
+    else if (db) db[e] = (float)sh[0];
+  }
 }
 
 bool embed_ok(long long rows, int IN, int E) {
@@ -153,6 +163,6 @@ extern "C" int psf_init_linear_bwd(const float* x, const float* dy, float* dW, f
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   const int per = out_features * (in_features + 1);
-  psf_embed_bwd_reduce_kernel<<<(per + 127) / 128, 128, 0, st>>>(part, dW, db, grid, out_features, in_features);
+  psf_embed_bwd_reduce_kernel<<<per, kEmbRedThreads, 0, st>>>(part, dW, db, grid, out_features, in_features);
   return (int)cudaGetLastError();
 }
