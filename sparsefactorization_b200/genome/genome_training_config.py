@@ -1,34 +1,10 @@
-"""PSF entry of the reference's genome configuration (Genome_Clf/genome_training_config.py:2-24 and its ``training``
-block): keyword arguments of ``genome.psf.PSFNet`` (``name`` is the reference's model selector and is not one of them)."""
+"""PSF entry of the reference's genome configuration (Genome_Clf/genome_training_config.py:2-24 and its ``training`` block),
+built with the same helper as the LRA tasks: ``config["DDcDNA"]["PSF"]`` are the keyword arguments of ``genome.psf.PSFNet`` plus
+``name`` (the reference's model selector), ``config["DDcDNA"]["training"]`` the loop settings.  The xformer baselines of that
+file are outside this path and are not listed."""
+from ..lra.psf_training_config import _task
 
-config = {
-    "DDcDNA": {
-        "PSF": {
-            "name": "psf",
-            "vocab_size": 6,
-            "embedding_size": 32,
-            "n_vec": 16384,
-            "n_W": 14,
-            "Ws": [32, 'GELU'],
-            "V": [32, 'GELU'],
-            "n_channels_V": 32,
-            "n_class": 2,
-            "pooling_type": "FLATTEN",
-            "head": ['linear'],
-            "use_cuda": True,
-            "use_residuals": False,
-            "dropout1_p": 0.2,
-            "dropout2_p": 0,
-            "dropout3_p": 0.8,
-            "init_embedding_weights": False,
-            "use_pos_embedding": False,
-        },
-        "training": {
-            "device_id": 0,
-            "batch_size": 16,
-            "learning_rate": 0.0001,
-            "eval_frequency": 1,
-            "num_train_steps": 100,
-        },
-    },
-}
+_t = _task(None, 6, 32, 16384, 14, 32, 32, 2, "FLATTEN", ['linear'], False, (0.2, 0, 0.8), False, False, 16, 0.0001, 100)
+_model = {"name": "psf", **{k: v for k, v in _t["model"].items() if k != "problem"}}
+
+config = {"DDcDNA": {"PSF": _model, "training": _t["training"]}}
